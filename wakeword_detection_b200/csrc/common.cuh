@@ -1,0 +1,191 @@
+// Shared declarations of the wwb200 library (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/wwb200.h"
+
+namespace wwb {
+
+constexpr int kFFT = 512;
+constexpr int kHop = 160;
+constexpr int kBins = 257;
+constexpr int kMel = 40;
+
+// ---- mel projection in CSR-by-segment form (built on the host from the dense matrix) ----
+// A "segment" is up to kSegTaps consecutive non-zeros of one mel band; a band owns a
+// contiguous range of segments so partial sums are combined in a fixed order.
+constexpr int kSegTaps = 8;
+struct MelTables {
+  int n_seg = 0;          // total segments
+  int* seg_band = nullptr;   // [n_seg]
+  int* seg_first = nullptr;  // [n_seg] index into tap arrays
+  int* seg_count = nullptr;  // [n_seg]
+  int* band_seg0 = nullptr;  // [kMel+1] first segment of each band
+  int* tap_bin = nullptr;    // [n_tap]
+  float* tap_w = nullptr;    // [n_tap]
+  float* bias = nullptr;     // [kMel]
+  int n_tap = 0;
+};
+
+struct CrnnWeights {   // device copies, fp32, layouts chosen for the kernels
+  float* conv_w = nullptr;   // [100][32]  (tap = kf*20+kt, chan)   transposed for coalesced reads
+  float* conv_b = nullptr;   // [32]
+  float* gru_w[4] = {};      // [in][96]   transposed: k-major rows
+  float* gru_u[4] = {};      // [32][96]
+  float* gru_bi[4] = {};     // [96]
+  float* gru_br[4] = {};     // [96]
+  float* det1_w = nullptr;   // [64][64] transposed [in][out]
+  float* det1_b = nullptr;
+  float* det2_w = nullptr;   // [n_out][64]
+  float* det2_b = nullptr;
+};
+
+struct WavenetWeights {
+  float* in_w = nullptr;     // [40][16] transposed
+  float* in_b = nullptr;     // [16]
+  float* bn_mul = nullptr;   // [24][16]
+  float* bn_add = nullptr;
+  int dilation[24] = {};
+  float* gate_w = nullptr;   // [24][48][32]: k = tap*16+in ; n<16 tanh, n>=16 sigmoid
+  float* gate_b = nullptr;   // [24][32]
+  float* rs_w = nullptr;     // [24][16][48]: n<16 residual (zeros for block 23), n>=16 skip
+  float* rs_b = nullptr;     // [24][48]
+  float* det1_w = nullptr;   // [32][32] transposed [in][out]
+  float* det1_b = nullptr;
+  float* det2_w = nullptr;   // [2][32]
+  float* det2_b = nullptr;
+};
+
+struct StreamState {
+  int64_t max_streams = 0;
+  int64_t max_chunk = 0;
+  int pend_cap = 0;      // samples of pending PCM kept per stream
+  int max_frames = 0;    // frames a single push can complete
+  int ring = 0;          // mel ring rows per stream (L + max_frames)
+  float* pending = nullptr;     // [S, pend_cap]
+  int32_t* n_pending = nullptr; // [S]
+  float* prev_sample = nullptr; // [S]
+  float* mel_ring = nullptr;    // [S, ring, 40]
+  int32_t* ring_head = nullptr; // [S] index of the oldest row of the current window
+  float* post_max = nullptr;    // [S]
+  uint8_t* was_speech = nullptr;// [S]
+  // per-push scratch
+  int32_t* n_new = nullptr;     // [S] frames analysed this push
+  int32_t* win_stream = nullptr;// [S*max_frames]
+  int32_t* win_start = nullptr; // [S*max_frames]
+  int32_t* win_slot = nullptr;  // [S] first window slot of the stream in this push
+  int32_t* n_win = nullptr;     // [1]
+  float* win_post = nullptr;    // [S*max_frames]
+};
+
+}  // namespace wwb
+
+struct wwb_ctx {
+  int device = 0;
+  int kind = 0;
+  int L = 0;          // mel_length
+  int n_out = 1;
+  int precision = WWB_PREC_F32;
+  int sm_count = 148;
+  float mel_floor = 1e-5f, mel_log_offset = 0.f, mel_scale = 0.5f;
+  wwb::MelTables mel;
+  float* hann = nullptr;       // [512] fp32 (np.hanning rounded from fp64)
+  float2* tw256 = nullptr;     // [256] W256^k
+  float2* tw512 = nullptr;     // [257] W512^k
+  wwb::CrnnWeights crnn;
+  wwb::WavenetWeights wn;
+  wwb::StreamState st;
+  // growable workspaces
+  void* ws[8] = {};
+  size_t ws_bytes[8] = {};
+  int64_t launches = 0;
+  std::string err;
+  std::vector<void*> owned;    // device allocations to free
+};
+
+namespace wwb {
+
+extern std::string g_create_error;
+
+int fail(wwb_ctx* ctx, int code, const char* fmt, ...);
+
+#define WWB_CUDA(ctx, expr)                                                               \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return wwb::fail(ctx, WWB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                 \
+                       cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+  } while (0)
+
+#define WWB_CHECK_LAUNCH(ctx)                                                             \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess)                                                                \
+      return wwb::fail(ctx, WWB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",             \
+                       cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+    (ctx)->launches++;                                                                    \
+  } while (0)
+
+// workspace slot `i` of at least `bytes`
+int workspace(wwb_ctx* ctx, int i, size_t bytes, void** out);
+
+// kernels' host launchers (one translation unit each)
+int launch_filter(wwb_ctx* ctx, const void* pcm, int dtype, int64_t S, int64_t N, int64_t pitch,
+                  float a, float* mel, cudaStream_t st);
+int launch_mel_from_mag(wwb_ctx* ctx, const float* mag, int64_t B, float* mel, cudaStream_t st);
+int launch_stream_filter(wwb_ctx* ctx, const int16_t* pcm, int64_t S, int64_t n,
+                         const uint8_t* is_speech, const uint8_t* is_active, float a,
+                         cudaStream_t st);
+int launch_stream_finish(wwb_ctx* ctx, int64_t S, const uint8_t* is_speech, const uint8_t* is_active,
+                         float threshold, float* post_out, int32_t* n_post_out, uint8_t* trigger_out,
+                         float* post_max_out, cudaStream_t st);
+int launch_stream_reset(wwb_ctx* ctx, const uint8_t* mask, int64_t S, cudaStream_t st);
+
+// window addressing shared by the encoders: window b reads rows
+//   mel + (stream(b)*ring + (start(b)+t) % ring) * 40,  t = 0..L-1
+struct WinMap {
+  const float* mel;
+  const int32_t* win_stream;  // optional explicit lists
+  const int32_t* win_start;
+  const int32_t* n_win_dev;   // optional device-side window count (streaming)
+  int64_t n_win;              // host-side count (upper bound when n_win_dev is set)
+  int64_t b0;                 // added to the window index (batch chunking)
+  int win_per_stream;         // regular grid: stream = b / wps, start = (b % wps)*hop
+  int hop;
+  int ring;                   // rows per stream
+};
+
+int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
+                         float* post, cudaStream_t st);
+int crnn_simt_detect(wwb_ctx* ctx, const float* enc, int64_t B, float* out, cudaStream_t st);
+int wavenet_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
+                            float* post, cudaStream_t st);
+int wavenet_simt_detect(wwb_ctx* ctx, const float* enc, int64_t B, float* out, cudaStream_t st);
+
+int launch_eval_counts(wwb_ctx* ctx, const float* post, const int64_t* seg_off, int64_t n_seg,
+                       const int32_t* halo_lo, const int32_t* halo_hi, int64_t n_total,
+                       const double* thr, int n_thr, int mode, int smooth, int64_t* counts,
+                       cudaStream_t st);
+
+__device__ __forceinline__ const float* win_row(const WinMap& wm, int64_t b, int t) {
+  int64_t s;
+  int start;
+  b += wm.b0;
+  if (wm.win_stream) {
+    s = wm.win_stream[b];
+    start = wm.win_start[b];
+  } else {
+    s = b / wm.win_per_stream;
+    start = (int)(b % wm.win_per_stream) * wm.hop;
+  }
+  int r = start + t;
+  if (r >= wm.ring) r -= wm.ring;
+  return wm.mel + (s * wm.ring + r) * (int64_t)kMel;
+}
+
+}  // namespace wwb
