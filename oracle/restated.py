@@ -85,7 +85,8 @@ def mel_stream(x: np.ndarray, w: Dict[str, np.ndarray], a: float = 0.0) -> np.nd
 # ----------------------------------------------------------------------------
 # CRNN  (architecture cross-check wwdetect/CRNN/model.py:21-56)
 def _sigmoid(x):
-    return (F32(1) / (F32(1) + np.exp(-x.astype(F32)))).astype(F32)
+    with np.errstate(over="ignore"):
+        return (F32(1) / (F32(1) + np.exp(-x.astype(F32)))).astype(F32)
 
 
 def crnn_conv(mel: np.ndarray, w: Dict[str, np.ndarray]) -> np.ndarray:

@@ -1,0 +1,430 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes `Engine`), against
+the CPU oracle on the same seeded inputs, against the committed golden vectors from the
+reference's own glue, and — at benchmark sizes — through size-independent properties.
+
+Tolerances: mel |d| <= 1e-4*max(|ref|,1) (bins within a factor 2 of the
+1e-5 energy floor are counted separately with a looser bound); encoder outputs and
+posteriors 1e-3 absolute; trigger decisions and FAR/FRR counts exact.
+"""
+import numpy as np
+import pytest
+
+from conftest import get_engine, load_weights
+from oracle import restated as R
+from wakeword_detection_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+MEL_RTOL = 1e-4
+POST_ATOL = 1e-3
+NEAR_FLOOR = 0.35          # 0.5*ln(2): energy below 2x the floor
+
+
+def check_mel(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape
+    tol = MEL_RTOL * np.maximum(np.abs(ref), 1.0)
+    err = np.abs(got - ref)
+    near = ref < NEAR_FLOOR
+    assert np.all(err[~near] <= tol[~near]), "mel error %.3e over tolerance (worst at ref=%.4f)" % (
+        err[~near].max(), ref[~near][np.argmax(err[~near])])
+    if near.any():
+        assert err[near].max() <= 2e-2, "near-floor mel error %.3e" % err[near].max()
+    return int(near.sum())
+
+
+# ------------------------------------------------------------------------------------ filter
+@pytest.mark.parametrize("cls", range(synth.N_CLASSES))
+def test_filter_int16_classes(cls, w_crnn):
+    eng = get_engine("CRNN")
+    n = 16000 + 37 * cls
+    pcm = synth.stream_int16(n, cls, seed=1, stream=cls)
+    mel = eng.filter(pcm[None]).cpu().numpy()[0]
+    ref = R.mel_stream(R.int16_to_float(pcm), w_crnn)
+    check_mel(mel, ref)
+
+
+def test_filter_silence_is_exact_zero():
+    eng = get_engine("CRNN")
+    mel = eng.filter(np.zeros((3, 4000), np.int16)).cpu().numpy()
+    assert mel.shape == (3, 22, 40) and np.all(mel == 0.0)
+
+
+@pytest.mark.parametrize("a", [0.0, 0.97])
+def test_filter_float_batch_preemphasis(a, w_crnn):
+    eng = get_engine("CRNN")
+    x = np.stack([np.clip(synth.stream_float(9000, c, 2, c), -1, 1) for c in (0, 2, 5)]).astype(np.float32)
+    mel = eng.filter(x, a).cpu().numpy()
+    for i in range(3):
+        check_mel(mel[i], R.mel_stream(x[i], w_crnn, a))
+
+
+def test_filter_golden_vectors(golden, w_crnn):
+    eng = get_engine("CRNN")
+    n = int(golden["filter_consumed_pe0"])
+    mel = eng.filter(golden["filter_in"][None, :n]).cpu().numpy()[0]
+    check_mel(mel, golden["filter_mel_pe0"])
+    mel = eng.filter(golden["filter_in"][None, :n], 0.97).cpu().numpy()[0]
+    check_mel(mel, golden["filter_mel_pe97"])
+
+
+def test_filter_edge_sizes(w_crnn):
+    eng = get_engine("CRNN")
+    assert eng.filter(np.zeros((2, 511), np.int16)).shape == (2, 0, 40)
+    assert eng.filter(np.zeros((0, 4000), np.int16)).shape == (0, 22, 40)
+    pcm = synth.stream_int16(512 + 160 * 16, 2, 3, 0)          # 17 frames: one full tile + 1
+    for n in (512, 671, 672, 512 + 160 * 15, 512 + 160 * 16):
+        mel = eng.filter(pcm[None, :n]).cpu().numpy()[0]
+        check_mel(mel, R.mel_stream(R.int16_to_float(pcm[:n]), w_crnn))
+    # unaligned rows (odd pitch) take the scalar load path
+    big = synth.batch_int16(3, 3001, seed=4)
+    mel = eng.filter(big).cpu().numpy()
+    for i in range(3):
+        check_mel(mel[i], R.mel_stream(R.int16_to_float(big[i]), w_crnn))
+
+
+def test_filter_mel_model_callable(w_crnn):
+    eng = get_engine("CRNN")
+    rng = np.random.default_rng(0)
+    mag = (rng.random((33, 257)) * 4).astype(np.float32)
+    mag[0] = 0
+    got = eng.mel_from_magnitude(mag).cpu().numpy()
+    check_mel(got, R.mel_from_magnitude(mag, w_crnn))
+
+
+def test_filter_full_size_properties():
+    """config 2 shape (many 2 s clips): doubling the PCM adds exactly 0.5*ln 2 to every mel
+    value above the floor; results do not depend on the batch a stream is in."""
+    import torch
+    eng = get_engine("CRNN")
+    S, N = 4096, 32000
+    pcm = synth.device_pcm(S, N, seed=7, device=eng.device)
+    pcm = torch.clamp(pcm, -16000, 16000)
+    mel1 = eng.filter(pcm)
+    mel2 = eng.filter(pcm * 2)
+    assert mel1.shape == (S, 197, 40)
+    mask = mel1 > 1.0
+    d = (mel2 - mel1)[mask]
+    assert float((d - 0.5 * np.log(2.0)).abs().max()) < 2e-4
+    sub = eng.filter(pcm[1000:1003].clone())
+    assert torch.equal(sub, mel1[1000:1003])
+    assert bool(torch.isfinite(mel1).all())
+
+
+# ------------------------------------------------------------------------------------ encoders
+def _windows(name, w, n_extra=24):
+    import os
+    from conftest import GOLDEN
+    adv = np.load(os.path.join(GOLDEN, "wake_%s_mel.npy" % name))
+    L = int(w["mel_length"])
+    mels = [R.mel_stream(np.clip(synth.stream_float(16000 * 3, c, 5, c), -1, 1).astype(np.float32), w)
+            for c in range(synth.N_CLASSES)]
+    rnd = [m[j:j + L] for m in mels for j in range(0, m.shape[0] - L, 41)][:n_extra]
+    zero = np.zeros((1, L, 40), np.float32)
+    return np.concatenate([adv, np.stack(rnd), zero]).astype(np.float32)
+
+
+@pytest.mark.parametrize("wname,name", [("CRNN", "crnn"), ("CRNN_arik_original", "crnn"), ("Wavenet", "wavenet")])
+def test_encode_detect_vs_oracle(wname, name):
+    w = load_weights(wname)
+    eng = get_engine(wname)
+    X = _windows(name, w)
+    if name == "wavenet":
+        X = X[::2]
+    enc = eng.encode(X)
+    ref_enc = R.encode(X, w)
+    assert np.abs(enc.cpu().numpy() - ref_enc).max() < POST_ATOL
+    det = eng.detect(enc).cpu().numpy()
+    ref_det = R.detect(ref_enc, w)
+    assert det.shape == ref_det.shape
+    assert np.abs(det - ref_det).max() < POST_ATOL
+    # detect on the oracle's encoder output as well (the two models are separate callables)
+    det2 = eng.detect(ref_enc).cpu().numpy()
+    assert np.abs(det2 - ref_det).max() < POST_ATOL
+    post = eng.posteriors(X.reshape(X.shape[0], X.shape[1], 40), hop=1).cpu().numpy()[:, 0]
+    ref = ref_det[:, -1]
+    assert np.abs(post - ref).max() < POST_ATOL
+    assert ref.max() > 0.9 and ref.min() < 0.1            # the set spans the posterior range
+    # decisions: exact outside the tolerance band around the threshold
+    band = np.abs(ref - 0.5) <= POST_ATOL
+    assert np.array_equal((post > 0.5)[~band], (ref > 0.5)[~band])
+
+
+def test_known_answers_on_device():
+    for wname, L, want in (("CRNN", 151, 0.00343328), ("CRNN_arik_original", 151, 0.13182628),
+                           ("Wavenet", 182, 0.12610082)):
+        eng = get_engine(wname)
+        p = eng.posteriors(np.zeros((2, L, 40), np.float32), hop=1).cpu().numpy()
+        assert p.shape == (2, 1) and np.abs(p - want).max() < 1e-5
+
+
+@pytest.mark.parametrize("wname", ["CRNN", "Wavenet"])
+def test_posteriors_sliding_windows(wname):
+    w = load_weights(wname)
+    eng = get_engine(wname)
+    L = int(w["mel_length"])
+    x = np.stack([np.clip(synth.stream_float(16000 * 2 + 777, c, 6, c), -1, 1) for c in (2, 0)]).astype(np.float32)
+    mel = eng.filter(x)
+    F = mel.shape[1]
+    p2 = eng.posteriors(mel, hop=2).cpu().numpy()
+    p1 = eng.posteriors(mel, hop=1).cpu().numpy()
+    assert p2.shape == (2, (F - L) // 2 + 1) and p1.shape == (2, F - L + 1)
+    np.testing.assert_array_equal(p1[:, ::2][:, :p2.shape[1]], p2)      # same windows, same bits
+    melh = mel.cpu().numpy()
+    j = np.arange(0, p2.shape[1], 7)
+    for s in range(2):
+        win = melh[s][(2 * j)[:, None] + np.arange(L)[None, :]]
+        assert np.abs(p2[s, j] - R.posterior(win, w)).max() < POST_ATOL
+    # too few frames -> no windows
+    assert eng.posteriors(mel[:, :L - 1], hop=2).shape == (2, 0)
+
+
+@pytest.mark.parametrize("wname,name", [("CRNN", "crnn"), ("Wavenet", "wavenet")])
+def test_pipeline_device_and_host(wname, name, wake_pcm):
+    w = load_weights(wname)
+    eng = get_engine(wname)
+    pcm = np.stack([wake_pcm[name][:32000], synth.stream_int16(32000, 2, 8, 1)])
+    post = eng.pipeline(pcm, hop=2).cpu().numpy()
+    host = eng.pipeline_host(pcm, hop=2)
+    np.testing.assert_array_equal(post, host)
+    for s in range(2):
+        mel = R.mel_stream(R.int16_to_float(pcm[s]), w)
+        nw = R.eval_windows(mel.shape[0], int(w["mel_length"]))
+        j = np.arange(0, nw, 3)
+        ref = R.posterior(mel[(2 * j)[:, None] + np.arange(int(w["mel_length"]))[None, :]], w)
+        assert np.abs(post[s, j] - ref).max() < POST_ATOL
+    assert post[0].max() > 0.9 and post[1].max() < 0.5
+
+
+def test_crnn_batch_config3_properties():
+    """config 3 shape: 8192 windows in one launch; the batch a window sits in must not
+    change its result, and window order is preserved."""
+    import torch
+    eng = get_engine("CRNN")
+    pcm = synth.device_pcm(64, 160 * 300 + 512, seed=3, device=eng.device)
+    mel = eng.filter(pcm)                                    # [64, 301, 40]
+    wins = mel.unfold(1, 151, 1).permute(0, 1, 3, 2)[:, :128].reshape(-1, 151, 40).contiguous()   # 8192
+    assert wins.shape[0] == 8192
+    p = eng.posteriors(wins, hop=1)[:, 0]
+    perm = torch.randperm(8192, device=eng.device)
+    pp = eng.posteriors(wins[perm].contiguous(), hop=1)[:, 0]
+    assert torch.equal(pp, p[perm])
+    assert torch.equal(eng.posteriors(wins[77:78].contiguous(), hop=1)[:, 0], p[77:78])
+    assert bool(((p >= 0) & (p <= 1)).all())
+
+
+def test_wavenet_config4_streaming_shape():
+    """config 4 shape: 4096 streams, one new mel frame per push (hop 1)."""
+    import torch
+    eng = get_engine("Wavenet")
+    S = 4096
+    if eng._stream_cap is None:
+        eng.stream_alloc(S, 320)
+    else:
+        eng.stream_reset()
+    pcm = synth.device_pcm(S, 160 * 6 + 512, seed=9, device=eng.device)
+    eng2 = get_engine("Wavenet")
+    mel = eng2.filter(pcm)                                   # 7 frames per stream
+    posts = []
+    o = 0
+    for n in (320, 192, 160, 160, 160, 160, 160, 160):
+        post, npost, trig, pmax = eng.stream_push(pcm[:, o:o + n].contiguous())
+        o += n
+        want = 0 if o < 512 else 1
+        assert int(npost.min()) == want and int(npost.max()) == want
+        if want:
+            posts.append(post[:, 0].clone())
+    assert len(posts) == 7
+    # window k = 182-k zeros + the first k mel frames: check two streams against the batch path
+    for k in (1, 7):
+        win = torch.zeros((2, 182, 40), device=eng.device)
+        win[:, 182 - k:] = mel[:2, :k]
+        ref = eng2.posteriors(win, hop=1)[:, 0]
+        assert float((posts[k - 1][:2] - ref).abs().max()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------ counters
+def test_eval_counts_vs_oracle(golden):
+    eng = get_engine("CRNN")
+    rng = np.random.default_rng(4)
+    traj = golden["pm_traj"].astype(np.float32)
+    for thr in (R.thresholds_eval(), R.thresholds_plot()):
+        sm = R.smooth_same(traj)
+        want = np.array([R.rising_edges(sm, t) for t in thr])
+        got = eng.eval_counts(traj, [0, traj.size], thr, "far_edges").cpu().numpy()
+        np.testing.assert_array_equal(got, want)
+        # several segments: counts add, nothing leaks across segment boundaries
+        cuts = [0, 900, 2500, 5000]
+        want2 = sum(np.array([R.rising_edges(R.smooth_same(traj[a:b]), t) for t in thr])
+                    for a, b in zip(cuts[:-1], cuts[1:]))
+        got2 = eng.eval_counts(traj, cuts, thr, "far_edges").cpu().numpy()
+        np.testing.assert_array_equal(got2, want2)
+        pos = rng.random(777).astype(np.float32)
+        seg = np.concatenate([[0], np.cumsum(rng.integers(1, 9, size=150))])
+        seg = seg[seg <= 777]
+        mx = np.array([pos[a:b].max() for a, b in zip(seg[:-1], seg[1:])])
+        want3 = np.array([(mx > t).sum() for t in thr])
+        got3 = eng.eval_counts(pos, seg, thr, "frr_max").cpu().numpy()
+        np.testing.assert_array_equal(got3, want3)
+
+
+def test_eval_counts_time_chunks_sum_to_whole(golden):
+    from wakeword_detection_b200 import dist as wd
+    eng = get_engine("CRNN")
+    traj = golden["pm_traj"].astype(np.float32)
+    thr = R.thresholds_eval()
+    whole = eng.eval_counts(traj, [0, traj.size], thr, "far_edges").cpu().numpy()
+    for world in (2, 4, 8):
+        total = np.zeros_like(whole)
+        for b, e, lo, hi in wd.time_chunks(traj.size, world):
+            part = traj[b - lo:e + hi]
+            total += eng.eval_counts(part, [0, part.size], thr, "far_edges", halo_lo=[lo], halo_hi=[hi]).cpu().numpy()
+        np.testing.assert_array_equal(total, whole)
+
+
+def test_eval_counts_errors():
+    eng = get_engine("CRNN")
+    with pytest.raises(ValueError):
+        eng.eval_counts(np.zeros(10, np.float32), [0, 5, 5, 10], [0.5, 0.6], "frr_max")     # empty clip
+    with pytest.raises(ValueError):
+        eng.eval_counts(np.zeros(10, np.float32), [0, 10], [0.6, 0.5], "far_edges")         # unsorted
+    with pytest.raises(ValueError):
+        eng.eval_counts(np.zeros(10, np.float32), [0, 10], [0.5], "far_edges")              # shorter than window
+
+
+# ------------------------------------------------------------------------------------ drop-ins
+@pytest.mark.parametrize("wname,name", [("CRNN", "crnn"), ("Wavenet", "wavenet")])
+def test_wakeword_trigger_replays_golden(wname, name, golden):
+    import os
+    from conftest import WEIGHTS
+    from wakeword_detection_b200.wakeword import WakewordTrigger
+    from wakeword_detection_b200.context import SpeechContext
+    trig = WakewordTrigger(model_dir=os.path.join(WEIGHTS, wname), model_type=wname)
+    assert trig.mel_length == (151 if name == "crnn" else 182) and trig.mel_width == 40
+    assert trig.hop_length == 160 and trig.encode_width == (64 if name == "crnn" else 32)
+    ctx = SpeechContext()
+    pcm, sp = golden["trig_%s_pcm" % name], golden["trig_%s_speech" % name]
+    posts, at = [], -1
+    for i in range(len(sp)):
+        ctx.is_speech = bool(sp[i])
+        trig(ctx, pcm[i * 320:(i + 1) * 320])
+        posts += list(trig.last_posteriors)
+        if ctx.is_active:
+            at = i
+            break
+    ref = golden["trig_%s_post" % name]
+    assert len(posts) == len(ref)
+    assert np.abs(np.array(posts) - ref).max() < POST_ATOL
+    assert at == int(golden["trig_%s_active_at" % name])
+    assert abs(trig._posterior_max - float(golden["trig_%s_post_max" % name])) < POST_ATOL
+    # once active the stage stops sampling (wakeword/tflite.py:139-140)
+    trig(ctx, pcm[:320])
+    assert len(trig.last_posteriors) == 0
+    # VAD fall resets the windows (:143-146)
+    ctx.is_active = False
+    ctx.is_speech = False
+    trig(ctx, pcm[:320])
+    assert trig._posterior_max == 0.0
+    with pytest.raises(ValueError):
+        WakewordTrigger(model_dir=os.path.join(WEIGHTS, wname), model_type=wname, fft_window_type="hamming")
+    trig.close()
+
+
+def test_multistream_trigger_vs_oracle(wake_pcm, w_crnn):
+    import os
+    from conftest import WEIGHTS
+    from wakeword_detection_b200.wakeword import MultiStreamTrigger
+    S = 5
+    ms = MultiStreamTrigger(os.path.join(WEIGHTS, "CRNN"), "CRNN", S, 320)
+    pcm = np.stack([np.concatenate([synth.stream_int16(1600 * s, 0, 2, s), wake_pcm["crnn"]])[:32000] for s in range(S)])
+    speech = np.ones((100, S), bool)
+    speech[:, 1] = False                       # stream 1: VAD never opens -> no posteriors
+    speech[40:44, 2] = False                   # stream 2: a VAD fall resets it mid-way
+    oracles = [R.TriggerOracle(w_crnn) for _ in range(S)]
+    active = np.zeros(S, bool)
+    for i in range(100):
+        out = ms.push(pcm[:, i * 320:(i + 1) * 320], speech[i], active)
+        npost = out["n_post"].cpu().numpy()
+        post = out["post"].cpu().numpy()
+        trig = out["trigger"].cpu().numpy().astype(bool)
+        for s in range(S):
+            o = oracles[s]
+            before = len(o.posteriors)
+            o.active = bool(active[s])
+            o(pcm[s, i * 320:(i + 1) * 320], bool(speech[i, s]))
+            new = np.array(o.posteriors[before:], np.float32)
+            assert npost[s] == len(new), (i, s)
+            if len(new):
+                assert np.abs(post[s, :len(new)] - new).max() < POST_ATOL
+                band = np.abs(new - 0.5) <= POST_ATOL
+                if not band.any():
+                    assert trig[s] == bool((new > 0.5).any() and not active[s])
+        active |= trig
+    assert active[0] and not active[1]
+    ms.close()
+
+
+def test_tflite_model_and_filter_dropins(golden, w_crnn):
+    import os
+    from conftest import WEIGHTS
+    from wakeword_detection_b200.models import TFLiteModel
+    from wakeword_detection_b200.filter import Filter
+    d = os.path.join(WEIGHTS, "CRNN")
+    f, e, dt = (TFLiteModel(os.path.join(d, n + ".tflite")) for n in ("filter", "encode", "detect"))
+    assert list(f.input_details[0]["shape"]) == [1, 257] and list(e.input_details[0]["shape"]) == [1, 40, 151, 1]
+    assert list(dt.input_details[0]["shape"]) == [1, 64] and list(dt.output_details[0]["shape"]) == [1, 1]
+    x = np.zeros((1, 40, 151, 1), np.float32)
+    post = dt(e(x)[0])[0]
+    assert post.shape == (1, 1) and abs(float(post[0][0]) - 0.00343328) < 1e-5
+    with pytest.raises(ValueError):
+        e(np.zeros((1, 151, 40, 1), np.float32))
+    with pytest.raises(ValueError):
+        f(np.zeros((1, 257), np.float64))
+    wd = os.path.join(WEIGHTS, "Wavenet")
+    we, wdt = TFLiteModel(os.path.join(wd, "encode.tflite")), TFLiteModel(os.path.join(wd, "detect.tflite"))
+    assert list(we.input_details[0]["shape"]) == [1, 182, 40]
+    out = wdt(we(np.zeros((1, 182, 40), np.float32))[0])[0]
+    np.testing.assert_allclose(out[0], [0.87389916, 0.12610082], atol=1e-5)
+
+    # Filter.filter_frame over the ragged chunks of the golden run
+    for tag, a in (("pe0", 0.0), ("pe97", 0.97)):
+        flt = Filter(pre_emphasis=a, model_dir=d)
+        assert flt.num_outputs() == 40
+        xin = golden["filter_in"].copy()
+        pos, mels, counts = 0, [], []
+        for n in [320, 320, 7, 1000, 1, 512, 160, 159, 3000] + [320] * 40:
+            chunk = xin[pos:pos + n].copy()
+            pos += n
+            if chunk.size == 0:
+                break
+            got = flt.filter_frame(chunk)
+            counts.append(len(got))
+            mels += got
+        np.testing.assert_array_equal(counts, golden["filter_counts_" + tag])
+        check_mel(np.stack(mels), golden["filter_mel_" + tag])
+    with pytest.raises(ValueError):
+        Filter(fft_window_type="hamming", model_dir=d)
+
+
+@pytest.mark.parametrize("wname,name", [("CRNN_arik_original", "crnn"), ("Wavenet", "wavenet")])
+def test_get_posterior_and_sweep_dropin(wname, name, golden):
+    import os
+    from conftest import WEIGHTS
+    from wakeword_detection_b200 import evaluate_models as EM, _cabi
+    d = os.path.join(WEIGHTS, wname)
+    typ = "CRNN" if name == "crnn" else "Wavenet"
+    clips = [golden["gp_%s_clip%d" % (name, i)] for i in range(3)]
+    fn = np.array(EM.get_posterior(d, typ, "false_negatives", clips, 20, 16000))
+    fa = np.array(EM.get_posterior(d, typ, "false_accepts", clips, 20, 16000))
+    assert np.abs(fn - golden["gp_%s_frr_max" % name]).max() < POST_ATOL
+    assert fa.shape == golden["gp_%s_far_traj" % name].shape
+    assert np.abs(fa - golden["gp_%s_far_traj" % name]).max() < POST_ATOL
+    # batching must not change anything (carry across clips is reproduced)
+    fa1 = np.array(EM.get_posterior(d, typ, "false_accepts", clips, 20, 16000, batch_clips=1))
+    np.testing.assert_array_equal(fa, fa1)
+    # the sweep on the reference's own posteriors gives the reference's own numbers
+    thr, FRR, FAR = EM.plot_FRR_FAR(golden["gp_%s_frr_max" % name], golden["gp_%s_far_traj" % name], 3, 0.5, typ,
+                                    engine=_cabi.engine_for_dir(d, typ), show=False)
+    np.testing.assert_array_equal(thr, golden["sweep_%s_thr" % name])
+    np.testing.assert_array_equal(FRR, golden["sweep_%s_frr" % name])
+    np.testing.assert_array_equal(FAR, golden["sweep_%s_far" % name])

@@ -1,0 +1,164 @@
+"""CPU tests of the host-side logic: ring buffer semantics, sharding, the counter
+all-reduce on gloo with world_size 2, window/clip bookkeeping."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE, ROOT
+from wakeword_detection_b200 import dist as wdist
+from wakeword_detection_b200.ring_buffer import RingBuffer
+from wakeword_detection_b200 import evaluate_models as EM
+
+
+def _drive(rb, ops, log):
+    for op, arg in ops:
+        try:
+            if op == "write":
+                rb.write(arg)
+            elif op == "read":
+                log.append(("read", rb.read().copy()))
+            elif op == "read_all":
+                log.append(("all", rb.read_all().copy()))
+            elif op == "seek":
+                rb.seek(arg)
+            elif op == "rewind":
+                rb.rewind()
+            elif op == "reset":
+                rb.reset()
+            elif op == "fill":
+                rb.fill(arg)
+            log.append((op, rb.is_empty, rb.is_full))
+        except IndexError as e:
+            log.append(("IndexError", str(e)))
+
+
+def test_ring_buffer_matches_reference_semantics():
+    rng = np.random.default_rng(0)
+    ops = [("fill", 0.0)]
+    for _ in range(400):
+        k = rng.integers(0, 10)
+        ops.append([("write", float(rng.random())), ("write", float(rng.random())), ("read", None),
+                    ("read_all", None), ("seek", int(rng.integers(0, 3))), ("rewind", None), ("reset", None),
+                    ("write", float(rng.random())), ("write", float(rng.random())), ("fill", float(k))][k])
+    mine = []
+    _drive(RingBuffer(shape=[5]), ops, mine)
+    # invariants that hold without the reference
+    rb = RingBuffer(shape=[3])
+    assert rb.capacity == 3 and rb.is_empty and not rb.is_full
+    for v in (1, 2, 3):
+        rb.write(v)
+    assert rb.is_full
+    with pytest.raises(IndexError):
+        rb.write(4)
+    rb.rewind().seek(1)
+    rb.write(4)
+    np.testing.assert_array_equal(rb.read_all(), [2, 3, 4])
+    assert rb.is_empty
+    with pytest.raises(IndexError):
+        rb.read()
+    path = os.path.join(REFERENCE, "spokestack", "ring_buffer.py")
+    if not os.path.exists(path):
+        return
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_ring_buffer", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    theirs = []
+    _drive(mod.RingBuffer(shape=[5]), ops, theirs)
+    assert len(mine) == len(theirs)
+    for a, b in zip(mine, theirs):
+        assert a[0] == b[0]
+        if a[0] in ("read", "all"):
+            np.testing.assert_array_equal(a[1], b[1])
+        else:
+            assert a[1:] == b[1:]
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 100, 4096):
+        for world in (1, 2, 3, 8):
+            spans = [wdist.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    chunks = wdist.time_chunks(1000, 4)
+    assert chunks[0][2] == 0 and chunks[-1][3] == 0 and chunks[1][2] == 16 and chunks[1][3] == 14
+
+
+def test_chunked_far_count_equals_whole(golden):
+    """Sharding one trajectory into time chunks with halos gives the same edge count
+    (checked here with the numpy oracle on logical ranks; the device version is in the gpu tests)."""
+    from oracle import restated as R
+    p = golden["pm_traj"]
+    thr = R.thresholds_eval()
+    sm = R.smooth_same(p)
+    whole = np.array([R.rising_edges(sm, t) for t in thr])
+    total = np.zeros_like(whole)
+    for b, e, lo, hi in wdist.time_chunks(len(p), 4):
+        seg = p[b - lo:e + hi]
+        sms = np.array([np.sum(seg[max(0, i - 15):i + 15] / 30.0) for i in range(len(seg))])
+        for ti, t in enumerate(thr):
+            above = sms > t
+            for i in range(lo, lo + (e - b)):
+                prev = above[i - 1] if i > 0 else False
+                total[ti] += int(above[i] and not prev)
+    np.testing.assert_array_equal(total, whole)
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from wakeword_detection_b200 import dist as wd
+    assert wd.rank_world() == (rank, world)
+    a = torch.arange(5, dtype=torch.int64) * (rank + 1)
+    b = torch.full((3,), rank + 10, dtype=torch.int64)
+    ra, rb = wd.all_reduce_counters(a, b)
+    if rank == 0:
+        out.put((ra.tolist(), rb.tolist()))
+    dist.destroy_process_group()
+
+
+def test_counter_all_reduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ra, rb = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ra == [0, 3, 6, 9, 12] and rb == [21, 21, 21]
+
+
+def test_eval_clip_padding_matches_oracle():
+    from oracle import restated as R
+    rng = np.random.default_rng(1)
+    for n in (1, 319, 320, 4321, 16000):
+        x = rng.standard_normal(n).astype(np.float32)
+        np.testing.assert_array_equal(EM._padded_stream(x, 16000, 320), R.eval_clip_samples(x))
+
+
+def test_wav_roundtrip(tmp_path):
+    pcm = (np.random.default_rng(2).standard_normal(4000) * 3000).astype(np.int16)
+    EM.concatenate_FA([pcm, pcm], 2, tmp_path / "x.wav")
+    x = EM.load_wav(tmp_path / "x.wav", 16000)
+    assert x.shape[0] == 8000 + 1600 and x.dtype == np.float32
+    np.testing.assert_array_equal(x[:4000], pcm.astype(np.float32) / 32768.0)
+    assert abs(EM.duration_test(tmp_path / "x.wav", 16000) - 0.6) < 1e-9
+    with pytest.raises(ValueError):
+        EM.load_wav(tmp_path / "x.wav", 8000)
+
+
+def test_parse_args_flags():
+    a = EM.parse_args(["--model_type", "Wavenet", "--models_dir", os.path.join(ROOT, "weights", "Wavenet")])
+    assert a.model_type == "Wavenet" and a.sample_rate == 16000 and a.frame_width == 20
+    assert a.neg_samples == "not_hey_snips_long.wav" and a.examine_audio is False
