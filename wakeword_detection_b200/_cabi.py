@@ -249,7 +249,7 @@ class Engine:
         S, N = pcm.shape
         F = self.num_frames(N)
         mel = out if out is not None else t.empty((S, F, self.n_mel), dtype=t.float32, device=self.device)
-        self._check(self.lib.wwb_filter(self.ctx, pcm.data_ptr(), dt, S, N, pcm.stride(0), float(pre_emphasis),
+        self._check(self.lib.wwb_filter(self.ctx, pcm.data_ptr(), dt, S, N, pcm.stride(0) if S > 1 else N, float(pre_emphasis),
                                         mel.data_ptr(), self._stream()))
         return mel
 
@@ -307,7 +307,7 @@ class Engine:
         S, N = pcm.shape
         nw = self.num_windows(self.num_frames(N), hop)
         post = out if out is not None else t.empty((S, nw), dtype=t.float32, device=self.device)
-        self._check(self.lib.wwb_pipeline(self.ctx, pcm.data_ptr(), dt, S, N, pcm.stride(0), float(pre_emphasis),
+        self._check(self.lib.wwb_pipeline(self.ctx, pcm.data_ptr(), dt, S, N, pcm.stride(0) if S > 1 else N, float(pre_emphasis),
                                           int(hop), post.data_ptr(), self._stream()))
         return post
 
