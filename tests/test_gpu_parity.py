@@ -131,10 +131,16 @@ def _windows(name, w, n_extra=24):
     return np.concatenate([adv, np.stack(rnd), zero]).astype(np.float32)
 
 
+TC_MODELS = ("CRNN", "CRNN_arik_original")     # models with a tensor-core path in this build
+
+
+@pytest.mark.parametrize("precision", ["f32", "tc"])
 @pytest.mark.parametrize("wname,name", [("CRNN", "crnn"), ("CRNN_arik_original", "crnn"), ("Wavenet", "wavenet")])
-def test_encode_detect_vs_oracle(wname, name):
+def test_encode_detect_vs_oracle(wname, name, precision):
+    if precision != "f32" and wname not in TC_MODELS:
+        pytest.skip("no tensor-core path for %s yet" % wname)
     w = load_weights(wname)
-    eng = get_engine(wname)
+    eng = get_engine(wname, precision)
     X = _windows(name, w)
     if name == "wavenet":
         X = X[::2]
@@ -155,6 +161,33 @@ def test_encode_detect_vs_oracle(wname, name):
     # decisions: exact outside the tolerance band around the threshold
     band = np.abs(ref - 0.5) <= POST_ATOL
     assert np.array_equal((post > 0.5)[~band], (ref > 0.5)[~band])
+
+
+@pytest.mark.parametrize("wname,name", [("CRNN", "crnn")])
+def test_tc_fast_mode_is_close_but_outside_parity(wname, name):
+    """single-fp16 operands: documented as outside the 1e-3 bound; must still be sane"""
+    w = load_weights(wname)
+    X = _windows(name, w)
+    ref = R.posterior(X, w)
+    fast = get_engine(wname, "tc_fast").posteriors(X, hop=1).cpu().numpy()[:, 0]
+    exact = get_engine(wname, "tc").posteriors(X, hop=1).cpu().numpy()[:, 0]
+    assert np.abs(fast - ref).max() < 2e-2
+    assert np.abs(exact - ref).max() < 2e-4 < POST_ATOL     # the split path is ~fp32
+    assert np.abs(exact - ref).max() <= np.abs(fast - ref).max()
+
+
+def test_tc_gemm_many_tiles_matches_f32_path():
+    """8192 windows (155648 GEMM rows, > 8 tiles per SM, ragged last tile) through both paths."""
+    import torch
+    e32, etc = get_engine("CRNN", "f32"), get_engine("CRNN", "tc")
+    pcm = synth.device_pcm(64, 160 * 300 + 512, seed=3, device=e32.device)
+    mel = e32.filter(pcm)
+    wins = mel.unfold(1, 151, 1).permute(0, 1, 3, 2)[:, :128].reshape(-1, 151, 40)[:8191].contiguous()
+    a = e32.posteriors(wins, hop=1)[:, 0]
+    b = etc.posteriors(wins, hop=1)[:, 0]
+    assert float((a - b).abs().max()) < 2e-4
+    enc_a, enc_b = e32.encode(wins[:300]), etc.encode(wins[:300])
+    assert float((enc_a - enc_b).abs().max()) < 2e-4
 
 
 def test_known_answers_on_device():

@@ -147,6 +147,12 @@ static int build_crnn(wwb_ctx* ctx, const wwb_weights* w) {
     }
     if ((rc = upload(ctx, wt, &C.gru_w[layer * 2]))) return rc;
     if ((rc = upload(ctx, bi, &C.gru_bi[layer * 2]))) return rc;
+    {  // tensor-core path: [192][in] (fwd units then bwd units), split into fp16 hi/lo stages
+      std::vector<float> w_nk((size_t)192 * in);
+      for (int dir = 0; dir < 2; ++dir)
+        memcpy(&w_nk[(size_t)dir * 96 * in], w->gru_w[layer * 2 + dir], sizeof(float) * 96 * in);
+      if ((rc = upload(ctx, pack_gemm_b(w_nk.data(), in, true), &C.gemm_b[layer]))) return rc;
+    }
     for (int dir = 0; dir < 2; ++dir) {
       if ((rc = upload(ctx, transposed(w->gru_u[layer * 2 + dir], 96, 32), &C.gru_u[layer * 2 + dir]))) return rc;
       if ((rc = upload(ctx, std::vector<float>(w->gru_br[layer * 2 + dir], w->gru_br[layer * 2 + dir] + 96),
@@ -206,8 +212,6 @@ static int build_wavenet(wwb_ctx* ctx, const wwb_weights* w) {
 static int run_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out, float* post,
                           cudaStream_t st) {
   if (ctx->kind == WWB_MODEL_NONE) return fail(ctx, WWB_ERR_STATE, "ctx holds a filter only (no encode/detect weights)");
-  if (ctx->precision != WWB_PREC_F32)
-    return fail(ctx, WWB_ERR_ARG, "precision %d not available in this build", ctx->precision);
   if (ctx->kind == WWB_MODEL_CRNN) return crnn_simt_posteriors(ctx, wm, enc_out, det_out, post, st);
   return wavenet_simt_posteriors(ctx, wm, enc_out, det_out, post, st);
 }
@@ -286,7 +290,10 @@ int wwb_destroy(wwb_ctx* ctx) {
 
 int wwb_set_precision(wwb_ctx* ctx, int precision) {
   if (!ctx) return WWB_ERR_ARG;
-  if (precision != WWB_PREC_F32) return fail(ctx, WWB_ERR_ARG, "precision %d not available in this build", precision);
+  if (precision != WWB_PREC_F32 && precision != WWB_PREC_TC && precision != WWB_PREC_TC_FAST)
+    return fail(ctx, WWB_ERR_ARG, "unknown precision %d", precision);
+  if (precision != WWB_PREC_F32 && ctx->kind == WWB_MODEL_WAVENET)
+    return fail(ctx, WWB_ERR_ARG, "tensor-core precision is not available for WaveNet in this build");
   ctx->precision = precision;
   return WWB_OK;
 }

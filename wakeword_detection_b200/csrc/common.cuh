@@ -43,6 +43,7 @@ struct CrnnWeights {   // device copies, fp32, layouts chosen for the kernels
   float* det1_b = nullptr;
   float* det2_w = nullptr;   // [n_out][64]
   float* det2_b = nullptr;
+  unsigned char* gemm_b[2] = {};   // tensor-core path: packed hi/lo fp16 weight stages (tc_gemm.cu), per layer
 };
 
 struct WavenetWeights {
@@ -160,6 +161,9 @@ struct WinMap {
   int ring;                   // rows per stream
 };
 
+std::vector<unsigned char> pack_gemm_b(const float* w_nk, int K, bool split);
+int tc_gemm_bias(wwb_ctx* ctx, const float* A, const unsigned char* Bpacked, const float* bias, float* C, int64_t M,
+                 int K, int nsplit, cudaStream_t st);
 int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
                          float* post, cudaStream_t st);
 int crnn_simt_detect(wwb_ctx* ctx, const float* enc, int64_t B, float* out, cudaStream_t st);

@@ -230,15 +230,25 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
     WWB_CHECK_LAUNCH(ctx);
     const int64_t M = nb * C_T;
     // both directions of a layer share one GEMM: Wt = [in][192]
-    sgemm_bias_kernel<<<dim3((unsigned)((M + 63) / 64), 3), 256, 0, st>>>((float*)conv, W.gru_w[0], W.gru_bi[0],
-                                                                          (float*)xw, M, 2 * C_G, C_FEAT);
-    WWB_CHECK_LAUNCH(ctx);
+    const bool tc = ctx->precision != WWB_PREC_F32;
+    const int nsplit = ctx->precision == WWB_PREC_TC ? 3 : 1;
+    if (tc) {
+      if ((rc = tc_gemm_bias(ctx, (float*)conv, W.gemm_b[0], W.gru_bi[0], (float*)xw, M, C_FEAT, nsplit, st))) return rc;
+    } else {
+      sgemm_bias_kernel<<<dim3((unsigned)((M + 63) / 64), 3), 256, 0, st>>>((float*)conv, W.gru_w[0], W.gru_bi[0],
+                                                                            (float*)xw, M, 2 * C_G, C_FEAT);
+      WWB_CHECK_LAUNCH(ctx);
+    }
     gru_rec_kernel<<<(unsigned)((nb + 3) / 4), 256, 0, st>>>((float*)xw, W.gru_u[0], W.gru_br[0], W.gru_u[1],
                                                             W.gru_br[1], (float*)s1, nullptr, nb, wm.n_win_dev);
     WWB_CHECK_LAUNCH(ctx);
-    sgemm_bias_kernel<<<dim3((unsigned)((M + 63) / 64), 3), 256, 0, st>>>((float*)s1, W.gru_w[2], W.gru_bi[2],
-                                                                          (float*)xw, M, 2 * C_G, 64);
-    WWB_CHECK_LAUNCH(ctx);
+    if (tc) {
+      if ((rc = tc_gemm_bias(ctx, (float*)s1, W.gemm_b[1], W.gru_bi[2], (float*)xw, M, 64, nsplit, st))) return rc;
+    } else {
+      sgemm_bias_kernel<<<dim3((unsigned)((M + 63) / 64), 3), 256, 0, st>>>((float*)s1, W.gru_w[2], W.gru_bi[2],
+                                                                            (float*)xw, M, 2 * C_G, 64);
+      WWB_CHECK_LAUNCH(ctx);
+    }
     gru_rec_kernel<<<(unsigned)((nb + 3) / 4), 256, 0, st>>>((float*)xw, W.gru_u[2], W.gru_br[2], W.gru_u[3],
                                                             W.gru_br[3], nullptr, enc, nb, wm.n_win_dev);
     WWB_CHECK_LAUNCH(ctx);
