@@ -131,7 +131,7 @@ def _windows(name, w, n_extra=24):
     return np.concatenate([adv, np.stack(rnd), zero]).astype(np.float32)
 
 
-TC_MODELS = ("CRNN", "CRNN_arik_original")     # models with a tensor-core path in this build
+TC_MODELS = ("CRNN", "CRNN_arik_original", "Wavenet")     # models with a tensor-core path
 
 
 @pytest.mark.parametrize("precision", ["f32", "tc"])
@@ -163,7 +163,7 @@ def test_encode_detect_vs_oracle(wname, name, precision):
     assert np.array_equal((post > 0.5)[~band], (ref > 0.5)[~band])
 
 
-@pytest.mark.parametrize("wname,name", [("CRNN", "crnn")])
+@pytest.mark.parametrize("wname,name", [("CRNN", "crnn"), ("Wavenet", "wavenet")])
 def test_tc_fast_mode_is_close_but_outside_parity(wname, name):
     """single-fp16 operands: documented as outside the 1e-3 bound; must still be sane"""
     w = load_weights(wname)
@@ -188,6 +188,23 @@ def test_tc_gemm_many_tiles_matches_f32_path():
     assert float((a - b).abs().max()) < 2e-4
     enc_a, enc_b = e32.encode(wins[:300]), etc.encode(wins[:300])
     assert float((enc_a - enc_b).abs().max()) < 2e-4
+
+
+def test_wavenet_tc_many_groups_matches_f32_path():
+    """4097 windows (1366 groups of 3, ragged last group, > 9 groups per SM) through both paths,
+    sliding hop-1 windows of real filter output; also the encoder output tensor."""
+    e32, etc = get_engine("Wavenet", "f32"), get_engine("Wavenet", "tc")
+    pcm = synth.device_pcm(17, 160 * 421 + 512, seed=5, device=e32.device)
+    mel = e32.filter(pcm)                      # [17, 422, 40] -> 241 windows per stream
+    a = e32.posteriors(mel, hop=1)
+    b = etc.posteriors(mel, hop=1)
+    assert a.shape == (17, 241)
+    assert float((a - b).abs().max()) < 2e-4
+    wins = mel.unfold(1, 182, 1).permute(0, 1, 3, 2)[:, :5].reshape(-1, 182, 40).contiguous()
+    ea, eb = e32.encode(wins), etc.encode(wins)
+    assert float((ea - eb).abs().max()) < 5e-4 * max(1.0, float(ea.abs().max()))
+    da, db = e32.detect(ea), etc.detect(eb)
+    assert float((da - db).abs().max()) < 2e-4
 
 
 def test_known_answers_on_device():

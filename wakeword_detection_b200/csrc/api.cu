@@ -198,6 +198,15 @@ static int build_wavenet(wwb_ctx* ctx, const wwb_weights* w) {
       for (int o = 0; o < 16; ++o) rb[b * 48 + o] = w->res_b[b * 16 + o];
     for (int o = 0; o < 32; ++o) rb[b * 48 + 16 + o] = w->skip_b[b * 32 + o];
   }
+  {
+    std::vector<unsigned char> blocks = wavenet_pack_blocks(gw.data(), gb.data(), rw.data(), rb.data(), w->bn_mul,
+                                                            w->bn_add, N.dilation);
+    if ((rc = upload(ctx, blocks, &N.tc_blocks))) return rc;
+    std::vector<float> in_w_kc = transposed(w->in_w, 16, 40);
+    std::vector<unsigned char> head = wavenet_pack_head(in_w_kc.data(), w->in_b, w->bn_mul, w->bn_add, w->det1_w,
+                                                        w->det1_b, w->det2_w, w->det2_b);
+    if ((rc = upload(ctx, head, &N.tc_head))) return rc;
+  }
   if ((rc = upload(ctx, gw, &N.gate_w))) return rc;
   if ((rc = upload(ctx, gb, &N.gate_b))) return rc;
   if ((rc = upload(ctx, rw, &N.rs_w))) return rc;
@@ -213,6 +222,7 @@ static int run_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float*
                           cudaStream_t st) {
   if (ctx->kind == WWB_MODEL_NONE) return fail(ctx, WWB_ERR_STATE, "ctx holds a filter only (no encode/detect weights)");
   if (ctx->kind == WWB_MODEL_CRNN) return crnn_simt_posteriors(ctx, wm, enc_out, det_out, post, st);
+  if (ctx->precision != WWB_PREC_F32) return wavenet_tc_posteriors(ctx, wm, enc_out, det_out, post, st);
   return wavenet_simt_posteriors(ctx, wm, enc_out, det_out, post, st);
 }
 
@@ -292,8 +302,6 @@ int wwb_set_precision(wwb_ctx* ctx, int precision) {
   if (!ctx) return WWB_ERR_ARG;
   if (precision != WWB_PREC_F32 && precision != WWB_PREC_TC && precision != WWB_PREC_TC_FAST)
     return fail(ctx, WWB_ERR_ARG, "unknown precision %d", precision);
-  if (precision != WWB_PREC_F32 && ctx->kind == WWB_MODEL_WAVENET)
-    return fail(ctx, WWB_ERR_ARG, "tensor-core precision is not available for WaveNet in this build");
   ctx->precision = precision;
   return WWB_OK;
 }

@@ -60,6 +60,8 @@ struct WavenetWeights {
   float* det1_b = nullptr;
   float* det2_w = nullptr;   // [2][32]
   float* det2_b = nullptr;
+  unsigned char* tc_blocks = nullptr;   // tensor-core path: per-block packed weights (wavenet_tc.cu)
+  unsigned char* tc_head = nullptr;     // resident head blob
 };
 
 struct StreamState {
@@ -169,6 +171,14 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
 int crnn_simt_detect(wwb_ctx* ctx, const float* enc, int64_t B, float* out, cudaStream_t st);
 int wavenet_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
                             float* post, cudaStream_t st);
+int wavenet_tc_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
+                          float* post, cudaStream_t st);
+std::vector<unsigned char> wavenet_pack_blocks(const float* gate_w, const float* gate_b, const float* rs_w,
+                                               const float* rs_b, const float* bn_mul, const float* bn_add,
+                                               const int* dilation);
+std::vector<unsigned char> wavenet_pack_head(const float* in_w_kc, const float* in_b, const float* bn_mul0,
+                                             const float* bn_add0, const float* det1_w_nk, const float* det1_b,
+                                             const float* det2_w, const float* det2_b);
 int wavenet_simt_detect(wwb_ctx* ctx, const float* enc, int64_t B, float* out, cudaStream_t st);
 
 int launch_eval_counts(wwb_ctx* ctx, const float* post, const int64_t* seg_off, int64_t n_seg,
