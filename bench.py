@@ -212,7 +212,7 @@ def main():
     ap.add_argument("--workload", default="sweep", choices=["sweep", "filter", "crnn", "wavenet"])
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (0 = workload default)")
     ap.add_argument("--seconds", type=float, default=0.0, help="seconds per stream (0 = workload default)")
-    ap.add_argument("--precision", default="f32", choices=["f32", "tc", "tc_fast"])
+    ap.add_argument("--precision", default="tc", choices=["f32", "tc", "tc_fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

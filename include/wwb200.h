@@ -186,6 +186,9 @@ int wwb_stream_reset(wwb_ctx* ctx, const uint8_t* mask_dev, int64_t n_streams, v
 
 /* number of kernels this library has launched on ctx since creation (bench accounting) */
 int64_t wwb_launch_count(const wwb_ctx* ctx);
+/* development aid: device buffer (>= 8 KB, zeroed) that instrumented kernels fill with
+ * clock64() timelines of their first work item; NULL disables it (default). */
+int wwb_debug_buffer(wwb_ctx* ctx, void* dev_buf);
 
 #ifdef __cplusplus
 }

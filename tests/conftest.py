@@ -70,7 +70,7 @@ def wake_pcm():
 _ENGINES = {}
 
 
-def get_engine(name, precision="f32"):
+def get_engine(name, precision="tc"):
     from wakeword_detection_b200 import _cabi
     key = (name, precision)
     if key not in _ENGINES:

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "wwb_stream_max_frames": (C.c_int, [_vp]),
     "wwb_stream_reset": (C.c_int, [_vp, _vp, _i64, _vp]),
     "wwb_launch_count": (_i64, [_vp]),
+    "wwb_debug_buffer": (C.c_int, [_vp, _vp]),
 }
 
 _lib = None
@@ -151,7 +152,7 @@ class Engine:
     """One wwb_ctx on one GPU.  All tensor arguments are torch CUDA tensors on that
     device (numpy arrays are uploaded); results are torch CUDA tensors."""
 
-    def __init__(self, weights: Dict[str, np.ndarray], device: int = 0, precision: str = "f32") -> None:
+    def __init__(self, weights: Dict[str, np.ndarray], device: int = 0, precision: str = "tc") -> None:
         import torch
 
         self.lib = load_library()
@@ -410,7 +411,7 @@ class Engine:
 _ENGINES: Dict[Tuple[str, str, int], Engine] = {}
 
 
-def engine_for_dir(model_dir: str, model_type: str, device: int = 0, precision: str = "f32") -> Engine:
+def engine_for_dir(model_dir: str, model_type: str, device: int = 0, precision: str = "tc") -> Engine:
     """One shared Engine per (model directory, kind, device) — the reference builds three
     interpreters per directory; here they share one context."""
     from . import weights as W

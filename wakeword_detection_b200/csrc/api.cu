@@ -483,4 +483,10 @@ int wwb_stream_reset(wwb_ctx* ctx, const uint8_t* mask, int64_t S, void* stream)
 
 int64_t wwb_launch_count(const wwb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int wwb_debug_buffer(wwb_ctx* ctx, void* dev_buf) {
+  if (!ctx) return WWB_ERR_ARG;
+  ctx->debug_buf = dev_buf;
+  return WWB_OK;
+}
+
 }  // extern "C"

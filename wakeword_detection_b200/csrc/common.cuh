@@ -107,6 +107,7 @@ struct wwb_ctx {
   void* ws[8] = {};
   size_t ws_bytes[8] = {};
   int64_t launches = 0;
+  void* debug_buf = nullptr;   // optional device buffer for kernel timeline dumps (wwb_debug_buffer)
   std::string err;
   std::vector<void*> owned;    // device allocations to free
 };

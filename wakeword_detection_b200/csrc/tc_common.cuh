@@ -40,7 +40,24 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
          | ((uint32_t)(M >> 4) << 24); // m_dim
 }
 
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- MMA -----------------------------------------------------------------------------
+// NOTE on issue cost (measured with tools/tc_latency.cu): tcgen05.mma takes its operands from
+// *uniform* registers.  If the descriptors are computed inside a divergent `if (lane == 0)` the
+// compiler wraps every MMA in a waterfall loop (~180 clk per MMA); computed by the whole
+// converged warp and issued under elect_one() a 128xNx16 MMA costs ~45 clk (N <= 64).
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the CTA.
 __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                            bool accumulate) {
@@ -53,6 +70,12 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uin
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
       : "memory");
+}
+
+// warp-collective forms: every lane passes the same (warp-uniform) operands, one lane issues
+__device__ __forceinline__ void mma_f16_ss_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             bool accumulate) {
+  if (elect_one()) mma_f16_ss(tmem_d, desc_a, desc_b, idesc, accumulate);
 }
 
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete
@@ -112,6 +135,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-defined time when the
+// phase is not complete yet; polling loops over several barriers must use test_wait)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must not hang the GPU.  ~2^26 polls (seconds) then trap.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t i = 0; i < (1u << 26); ++i)
@@ -129,6 +167,17 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
 }
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// Cheap split of a PAIR of values: hi = x with the mantissa truncated to 10 bits (exactly an
+// fp16 value for |x| in the normal fp16 range), lo = x - hi (exact in fp32), each pair packed
+// by one cvt.rn.f16x2.  |x - (hi + lo)| <= 2^-21 |x| (plus 6e-8 absolute below 6e-5).
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+  const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  __half2 h = __floats2half2_rn(ah, bh);
+  __half2 l = __floats2half2_rn(a - ah, b - bh);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
 }  // namespace tc
@@ -148,17 +197,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
+
 
 }  // namespace tc
 }  // namespace wwb

@@ -109,7 +109,7 @@ tc_gemm_bias_kernel(const float* __restrict__ A, const unsigned char* __restrict
         const int s = it % G_STAGES;
         mbar_wait(&sm.full[s], (it / G_STAGES) & 1);
         fence_after_sync();
-        if (lane == 0) {
+        {
           const uint32_t a_hi = smem_u32(sm.a[s]), a_lo = a_hi + G_CH * 128 * 16;
           const uint32_t b_hi = smem_u32(sm.b[s]), b_lo = b_hi + G_CH * G_N * 16;
 #pragma unroll
@@ -117,14 +117,16 @@ tc_gemm_bias_kernel(const float* __restrict__ A, const unsigned char* __restrict
             const uint32_t ao = kk * 2 * 128 * 16, bo = kk * 2 * G_N * 16;
             const uint64_t dah = make_desc(a_hi + ao, 128 * 16, 128), dal = make_desc(a_lo + ao, 128 * 16, 128);
             const uint64_t dbh = make_desc(b_hi + bo, G_N * 16, 128), dbl = make_desc(b_lo + bo, G_N * 16, 128);
-            mma_f16_ss(d, dah, dbh, idesc, (ks | kk) != 0);
+            mma_f16_ss_w(d, dah, dbh, idesc, (ks | kk) != 0);
             if (nsplit == 3) {
-              mma_f16_ss(d, dal, dbh, idesc, true);
-              mma_f16_ss(d, dah, dbl, idesc, true);
+              mma_f16_ss_w(d, dal, dbh, idesc, true);
+              mma_f16_ss_w(d, dah, dbl, idesc, true);
             }
           }
-          mma_commit(&sm.empty[s]);
-          if (ks == n_ks - 1) mma_commit(&sm.accfull[ab]);
+          if (elect_one()) {
+            mma_commit(&sm.empty[s]);
+            if (ks == n_ks - 1) mma_commit(&sm.accfull[ab]);
+          }
         }
         __syncwarp();
       }

@@ -33,9 +33,10 @@ constexpr int WN_PU = WN_UROWS * 16;          // bytes per U chunk panel
 constexpr int WN_PG = WN_ROWS * 16;           // bytes per G chunk panel
 constexpr int WN_EPI_WARPS = WN_NT * 4;       // 20
 constexpr int WN_EPI_THREADS = WN_EPI_WARPS * 32;
-constexpr int WN_THREADS = (WN_EPI_WARPS + 2) * 32;   // + MMA warp + loader warp = 704
+constexpr int WN_THREADS = (WN_EPI_WARPS + 1) * 32;   // + MMA/loader warp = 672 (leaves 96 registers per thread)
 constexpr int WN_WBLK = 9728;                 // bytes of one block's weight blob
 constexpr int WN_GATE_B = 6144, WN_RS_B = 3072;
+constexpr int WN_WST = 4;                     // weight ring stages
 constexpr int WN_TMEM_TILE = 96;              // columns per tile: gate 32 @0, res/skip 48 @32
 
 // resident head blob (floats unless noted)
@@ -53,10 +54,10 @@ struct WnHead {
 struct WnSmem {
   unsigned char U[2 * 2 * WN_PU];          // [plane][chunk][row]
   unsigned char Gb[2 * 2 * WN_PG];
-  unsigned char W[2][WN_WBLK];
+  unsigned char W[WN_WST][WN_WBLK];
   WnHead head;
   uint64_t bar_u[WN_NT], bar_gate[WN_NT], bar_g[WN_NT], bar_rs[WN_NT];
-  uint64_t wfull[2], wempty[2];
+  uint64_t wfull[WN_WST];
   uint32_t tmem_base;
   int zmax[WN_G][2];
 };
@@ -67,10 +68,14 @@ struct WnTcParams {
   const WnHead* head;
   int L;
   int nsplit;
+  int dil[24];                  // dilation per block (kernel-parameter space keeps it in uniform registers)
   float* enc_out;
   float* det_out;
   float* post;
+  long long* dbg;   // optional timeline dump (block 0, first group): [6 roles][24 blocks][4 events]
 };
+
+#define WN_DBG(role, k, ev) do { if (P.dbg && blockIdx.x == 0 && grp == 0) P.dbg[((role) * 24 + (k)) * 4 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -83,11 +88,11 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 // tanh(a) * sigmoid(b) with two ex2 and one rcp
-__device__ __forceinline__ float gate_fn(float a, float b) {
-  a = fminf(fmaxf(a, -15.f), 15.f);
-  b = fminf(fmaxf(b, -30.f), 30.f);
-  const float ea = ex2_approx(a * -2.8853900817779268f);   // e^(-2a)
-  const float eb = ex2_approx(b * -1.4426950408889634f);   // e^(-b)
+// `a2` = -2*log2(e)*a and `b2` = -log2(e)*b arrive pre-scaled (bias folded in by an FFMA).
+// Only e^(-2a) can make the quotient inf/inf, so only it is clamped (tanh is +-1 to 1e-13 there).
+__device__ __forceinline__ float gate_fn(float a2, float b2) {
+  const float ea = ex2_approx(fminf(a2, 43.f));   // e^(-2a), a >= -14.9
+  const float eb = ex2_approx(b2);                // e^(-b); inf -> rcp(inf) = 0 -> g = 0
   return (1.f - ea) * rcp_approx((1.f + ea) * (1.f + eb));
 }
 
@@ -102,11 +107,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 
 // 8 fp32 -> one 16-byte chunk of hi halves and one of lo halves
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
-  __half h[8], l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) split_f16(x[i], h[i], l[i]);
-  hi = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
-  lo = make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7]));
+  split_pair(x[0], x[1], hi.x, lo.x);
+  split_pair(x[2], x[3], hi.y, lo.y);
+  split_pair(x[4], x[5], hi.z, lo.z);
+  split_pair(x[6], x[7], hi.w, lo.w);
+}
+__device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
 __device__ __forceinline__ void atomic_max_float(int* addr, float v) {
@@ -134,7 +142,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     for (int i = 0; i < WN_NT; ++i) {
       mbar_init(&sm.bar_u[i], 4); mbar_init(&sm.bar_gate[i], 1); mbar_init(&sm.bar_g[i], 4); mbar_init(&sm.bar_rs[i], 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sm.wfull[s], 1); mbar_init(&sm.wempty[s], WN_EPI_WARPS); }
+    for (int s = 0; s < WN_WST; ++s) mbar_init(&sm.wfull[s], 1);
     mbar_fence_init();
   }
   if (warp == WN_EPI_WARPS) tmem_alloc(&sm.tmem_base, 512);
@@ -207,22 +215,26 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       }
 
       for (int k = 0; k < 24; ++k, ++n_w) {
-        const int ws = n_w & 1;
-        mbar_wait(&sm.wfull[ws], (n_w >> 1) & 1);
+        const int ws = n_w % WN_WST;
+        mbar_wait(&sm.wfull[ws], (n_w / WN_WST) & 1);
         const float* wf = reinterpret_cast<const float*>(sm.W[ws] + WN_GATE_B + WN_RS_B);   // gate_b[32] rs_b[48] bn_mul[16] bn_add[16]
         // ---- epilogue 1: gated activation ----
         mbar_wait(&sm.bar_gate[tile], n_gate & 1);
         ++n_gate;
         fence_after_sync();
+        if (q == 0 && lane == 0) WN_DBG(tile, k, 0);
 #pragma unroll
         for (int h8 = 0; h8 < 2; ++h8) {
           float at[8], as[8];
           tmem_ld8(tbase + h8 * 8, at);
           tmem_ld8(tbase + 16 + h8 * 8, as);
           tmem_ld_wait();
-          float g[8];
+          float g[8], bt[8], bs[8];
+          ld8f(wf + h8 * 8, bt);
+          ld8f(wf + 16 + h8 * 8, bs);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = gate_fn(at[i] + wf[h8 * 8 + i], as[i] + wf[16 + h8 * 8 + i]);
+          for (int i = 0; i < 8; ++i)
+            g[i] = gate_fn(fmaf(at[i], -2.8853900817779268f, bt[i]), fmaf(as[i], -1.4426950408889634f, bs[i]));
           uint4 hi, lo;
           split8(g, hi, lo);
           *reinterpret_cast<uint4*>(Grow + h8 * WN_PG) = hi;
@@ -232,11 +244,13 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.bar_g[tile]);
+        if (q == 0 && lane == 0) WN_DBG(tile, k, 1);
 
         // ---- epilogue 2: residual + skip, next block's BN ----
         mbar_wait(&sm.bar_rs[tile], n_rs & 1);
         ++n_rs;
         fence_after_sync();
+        if (q == 0 && lane == 0) WN_DBG(tile, k, 2);
         const bool last = (k == 23);
 #pragma unroll
         for (int h8 = 0; h8 < 2; ++h8) {
@@ -244,12 +258,15 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           tmem_ld8(tbase + 32 + h8 * 8, r);
           tmem_ld_wait();
           if (!last) {
-            float u[8];
+            float u[8], br[8], bm[8], ba[8];
+            ld8f(wf + 32 + h8 * 8, br);
+            ld8f(wf + 80 + h8 * 8, bm);
+            ld8f(wf + 96 + h8 * 8, ba);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int c = h8 * 8 + i;
-              x[c] = fmaxf(r[i] + wf[32 + c], 0.f) + x[c];
-              u[i] = __fadd_rn(__fmul_rn(x[c], wf[80 + c]), wf[96 + c]);
+              x[c] = fmaxf(r[i] + br[i], 0.f) + x[c];
+              u[i] = fmaf(x[c], bm[i], ba[i]);
             }
             if (valid) {
               uint4 hi, lo;
@@ -261,11 +278,12 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         }
 #pragma unroll
         for (int h8 = 0; h8 < 4; ++h8) {
-          float s[8];
+          float s[8], bk[8];
           tmem_ld8(tbase + 48 + h8 * 8, s);
+          ld8f(wf + 48 + h8 * 8, bk);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) skip[h8 * 8 + i] += fmaxf(s[i] + wf[48 + h8 * 8 + i], 0.f);
+          for (int i = 0; i < 8; ++i) skip[h8 * 8 + i] += fmaxf(s[i] + bk[i], 0.f);
         }
         if (last) {
           // detect input: ReLU(skip) hi/lo; channels 0-15 -> G panels, 16-31 -> U panels
@@ -288,10 +306,8 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         fence_before_sync();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&sm.bar_u[tile]);
-          mbar_arrive(&sm.wempty[ws]);
-        }
+        if (lane == 0) mbar_arrive(&sm.bar_u[tile]);
+        if (q == 0 && lane == 0) WN_DBG(tile, k, 3);
       }
 
       if (P.enc_out && valid) {
@@ -336,67 +352,92 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       }
       epi_bar_sync();
     }
-  } else if (warp == WN_EPI_WARPS) {
-    // =========================== MMA issuer ===========================
+  } else {
+    // =========================== MMA issuer + weight loader ===========================
+    // Per block: all five gate GEMMs first (each as soon as its tile's U is ready), then the
+    // five res/skip GEMMs (each as soon as its tile's g is ready).  rs(k,i) is therefore always
+    // issued after gate(k,i+1), which reads the last rows of tile i's U through the row-shifted
+    // taps and must finish before epilogue 2 of (k,i) overwrites them (tcgen05 ops of one thread
+    // complete in order).  Tiles run staggered: while tile 4 is still in epilogue 1 of block k,
+    // tile 0 is already in epilogue 2, which keeps the SFU and FMA pipes both busy.
+    // The weight ring is refilled right after the gate GEMMs of block k are issued: by then
+    // every tile has finished block k-1, so the other stage is free.
     const uint32_t idesc_gate = make_idesc_f16(128, 32), idesc_rs = make_idesc_f16(128, 48);
-    uint32_t n_u = 0, n_g = 0, n_w = 0;
+    const uint32_t hb = smem_u32(sm.head.det1_B);
+    uint32_t n_u = 0, n_g = 0, n_w = 0, n_load = 0;
+    uint32_t my_groups = 0;
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) ++my_groups;
+    const uint32_t total_loads = my_groups * 24;
+    // prologue: fill WN_WST-1 stages
+    for (; n_load < (uint32_t)(WN_WST - 1) && n_load < total_loads; ++n_load)
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&sm.wfull[n_load % WN_WST], WN_WBLK);
+        bulk_g2s(sm.W[n_load % WN_WST], P.wblob + (size_t)(n_load % 24) * WN_WBLK, WN_WBLK, &sm.wfull[n_load % WN_WST]);
+      }
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
       for (int k = 0; k < 24; ++k, ++n_w) {
-        const int ws = n_w & 1;
-        mbar_wait(&sm.wfull[ws], (n_w >> 1) & 1);
-        const int d = (int)reinterpret_cast<const float*>(sm.W[ws] + WN_GATE_B + WN_RS_B)[112];   // dilation stored as float
+        const int ws = n_w % WN_WST;
+        mbar_wait(&sm.wfull[ws], (n_w / WN_WST) & 1);
+        const int d = P.dil[k];
         const uint32_t wb = smem_u32(sm.W[ws]);
-        for (int i = 0; i <= WN_NT; ++i) {
-          if (i < WN_NT) {
-            mbar_wait(&sm.bar_u[i], n_u & 1);
-            fence_after_sync();
-            if (lane == 0) {
-              const uint32_t dst = tmem + i * WN_TMEM_TILE;
-              bool first = true;
+        for (int i = 0; i < WN_NT; ++i) {
+          mbar_wait(&sm.bar_u[i], n_u & 1);
+          fence_after_sync();
+          {
+            const uint32_t dst = tmem + i * WN_TMEM_TILE;
 #pragma unroll
-              for (int tap = 0; tap < 3; ++tap) {
-                const uint32_t arow = (uint32_t)(16 + i * 128 - (2 - tap) * d) * 16;
-                const uint64_t ah = make_desc(uU + arow, WN_PU, 128), al = make_desc(uU + 2 * WN_PU + arow, WN_PU, 128);
-                const uint64_t bh = make_desc(wb + tap * 2 * 512, 512, 128), bl = make_desc(wb + 3072 + tap * 2 * 512, 512, 128);
-                mma_f16_ss(dst, ah, bh, idesc_gate, !first);
-                first = false;
-                if (nsplit == 3) {
-                  mma_f16_ss(dst, al, bh, idesc_gate, true);
-                  mma_f16_ss(dst, ah, bl, idesc_gate, true);
-                }
-              }
-              mma_commit(&sm.bar_gate[i]);
-            }
-            __syncwarp();
-          }
-          if (i >= 1) {
-            const int j = i - 1;
-            mbar_wait(&sm.bar_g[j], n_g & 1);
-            fence_after_sync();
-            if (lane == 0) {
-              const uint32_t dst = tmem + j * WN_TMEM_TILE + 32;
-              const uint32_t arow = (uint32_t)(j * 128) * 16;
-              const uint64_t ah = make_desc(uG + arow, WN_PG, 128), al = make_desc(uG + 2 * WN_PG + arow, WN_PG, 128);
-              const uint64_t bh = make_desc(wb + WN_GATE_B, 768, 128), bl = make_desc(wb + WN_GATE_B + 1536, 768, 128);
-              mma_f16_ss(dst, ah, bh, idesc_rs, false);
+            for (int tap = 0; tap < 3; ++tap) {
+              const uint32_t arow = (uint32_t)(16 + i * 128 - (2 - tap) * d) * 16;
+              const uint64_t ah = make_desc(uU + arow, WN_PU, 128), al = make_desc(uU + 2 * WN_PU + arow, WN_PU, 128);
+              const uint64_t bh = make_desc(wb + tap * 2 * 512, 512, 128), bl = make_desc(wb + 3072 + tap * 2 * 512, 512, 128);
+              mma_f16_ss_w(dst, ah, bh, idesc_gate, tap != 0);
               if (nsplit == 3) {
-                mma_f16_ss(dst, al, bh, idesc_rs, true);
-                mma_f16_ss(dst, ah, bl, idesc_rs, true);
+                mma_f16_ss_w(dst, al, bh, idesc_gate, true);
+                mma_f16_ss_w(dst, ah, bl, idesc_gate, true);
               }
-              mma_commit(&sm.bar_rs[j]);
             }
-            __syncwarp();
+            if (elect_one()) mma_commit(&sm.bar_gate[i]);
+            if (lane == 0 && i == 0) WN_DBG(5, k, 0);
+            if (lane == 0 && i == WN_NT - 1) WN_DBG(5, k, 1);
           }
+          __syncwarp();
         }
         ++n_u;
+        // all tiles have finished block k-1, so the stage that held its weights is free:
+        // refill it with the block WN_WST-1 ahead (bulk copies take ~2.4 us, i.e. > one block)
+        if (n_load < total_loads) {
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&sm.wfull[n_load % WN_WST], WN_WBLK);
+            bulk_g2s(sm.W[n_load % WN_WST], P.wblob + (size_t)(n_load % 24) * WN_WBLK, WN_WBLK, &sm.wfull[n_load % WN_WST]);
+          }
+          ++n_load;
+        }
+        for (int i = 0; i < WN_NT; ++i) {
+          mbar_wait(&sm.bar_g[i], n_g & 1);
+          fence_after_sync();
+          {
+            const uint32_t dst = tmem + i * WN_TMEM_TILE + 32;
+            const uint32_t arow = (uint32_t)(i * 128) * 16;
+            const uint64_t ah = make_desc(uG + arow, WN_PG, 128), al = make_desc(uG + 2 * WN_PG + arow, WN_PG, 128);
+            const uint64_t bh = make_desc(wb + WN_GATE_B, 768, 128), bl = make_desc(wb + WN_GATE_B + 1536, 768, 128);
+            mma_f16_ss_w(dst, ah, bh, idesc_rs, false);
+            if (nsplit == 3) {
+              mma_f16_ss_w(dst, al, bh, idesc_rs, true);
+              mma_f16_ss_w(dst, ah, bl, idesc_rs, true);
+            }
+            if (elect_one()) mma_commit(&sm.bar_rs[i]);
+            if (lane == 0 && i == 0) WN_DBG(5, k, 2);
+            if (lane == 0 && i == WN_NT - 1) WN_DBG(5, k, 3);
+          }
+          __syncwarp();
+        }
         ++n_g;
       }
       // detect head: D[128,32] = ReLU(skip)[128,32] * W1^T ; k-step 0 from G panels, k-step 1 from U panels
-      const uint32_t hb = smem_u32(sm.head.det1_B);
       for (int i = 0; i < WN_NT; ++i) {
         mbar_wait(&sm.bar_u[i], n_u & 1);
         fence_after_sync();
-        if (lane == 0) {
+        {
           const uint32_t dst = tmem + i * WN_TMEM_TILE;
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
@@ -404,29 +445,17 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             const uint32_t pl = kk == 0 ? WN_PG : WN_PU;
             const uint64_t ah = make_desc(abase, pl, 128), al = make_desc(abase + 2 * pl, pl, 128);
             const uint64_t bh = make_desc(hb + kk * 2 * 512, 512, 128), bl = make_desc(hb + 2048 + kk * 2 * 512, 512, 128);
-            mma_f16_ss(dst, ah, bh, idesc_gate, kk != 0);
+            mma_f16_ss_w(dst, ah, bh, idesc_gate, kk != 0);
             if (nsplit == 3) {
-              mma_f16_ss(dst, al, bh, idesc_gate, true);
-              mma_f16_ss(dst, ah, bl, idesc_gate, true);
+              mma_f16_ss_w(dst, al, bh, idesc_gate, true);
+              mma_f16_ss_w(dst, ah, bl, idesc_gate, true);
             }
           }
-          mma_commit(&sm.bar_gate[i]);
+          if (elect_one()) mma_commit(&sm.bar_gate[i]);
         }
         __syncwarp();
       }
       ++n_u;
-    }
-  } else {
-    // =========================== weight loader ===========================
-    if (lane == 0) {
-      uint32_t n_w = 0;
-      for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
-        for (int k = 0; k < 24; ++k, ++n_w) {
-          const int ws = n_w & 1;
-          mbar_wait(&sm.wempty[ws], ((n_w >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&sm.wfull[ws], WN_WBLK);
-          bulk_g2s(sm.W[ws], P.wblob + (size_t)k * WN_WBLK, WN_WBLK, &sm.wfull[ws]);
-        }
     }
   }
   fence_before_sync();
@@ -463,7 +492,8 @@ std::vector<unsigned char> wavenet_pack_blocks(const float* gate_w, const float*
         put_split(out, off, off + 1536, rs_w[((size_t)b * 16 + k) * 48 + n], true);
       }
     float f[113] = {0};
-    for (int n = 0; n < 32; ++n) f[n] = gate_b[b * 32 + n];
+    for (int n = 0; n < 32; ++n)   // pre-scaled for gate_fn: tanh half by -2*log2(e), sigmoid half by -log2(e)
+      f[n] = (float)((double)gate_b[b * 32 + n] * (n < 16 ? -2.8853900817779268 : -1.4426950408889634));
     for (int n = 0; n < 48; ++n) f[32 + n] = rs_b[b * 48 + n];
     if (b < 23)
       for (int c = 0; c < 16; ++c) { f[80 + c] = bn_mul[(b + 1) * 16 + c]; f[96 + c] = bn_add[(b + 1) * 16 + c]; }
@@ -505,7 +535,9 @@ int wavenet_tc_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float*
   P.head = reinterpret_cast<const WnHead*>(ctx->wn.tc_head);
   P.L = ctx->L;
   P.nsplit = ctx->precision == WWB_PREC_TC ? 3 : 1;
+  for (int b = 0; b < 24; ++b) P.dil[b] = ctx->wn.dilation[b];
   P.enc_out = enc_out; P.det_out = det_out; P.post = post;
+  P.dbg = reinterpret_cast<long long*>(ctx->debug_buf);
   const size_t smem = sizeof(WnSmem) + 128;
   WWB_CUDA(ctx, cudaFuncSetAttribute(wavenet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_groups = (wm.n_win + WN_G - 1) / WN_G;

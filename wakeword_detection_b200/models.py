@@ -45,7 +45,7 @@ class TFLiteModel:
             raise ValueError("Could not open '%s'." % model_path)
         self.role = role
         device = int(kwargs.pop("device", 0))
-        precision = kwargs.pop("precision", "f32")
+        precision = kwargs.pop("precision", "tc")
         kind = _kind_of_dir(model_dir)
         if role != "filter" and not kind:
             raise ValueError("Could not open '%s': no encode/detect weights in %s" % (model_path, model_dir))

@@ -30,7 +30,7 @@ class MultiStreamTrigger:
 
     def __init__(self, model_dir: str, model_type: str, n_streams: int, chunk_samples: int = 320,
                  pre_emphasis: float = 0.0, posterior_threshold: float = 0.5, device: int = 0,
-                 precision: str = "f32") -> None:
+                 precision: str = "tc") -> None:
         from . import weights as W
         self.engine = _cabi.Engine(W.load_model_dir(model_dir, model_type), device, precision)
         self.n_streams = int(n_streams)
@@ -62,7 +62,7 @@ class WakewordTrigger:
             raise ValueError("Invalid fft_window_type")
         self.model_type = model_type.upper()
         device = int(kwargs.pop("device", 0))
-        precision = kwargs.pop("precision", "f32")
+        precision = kwargs.pop("precision", "tc")
         max_chunk = int(kwargs.pop("max_chunk_samples", 1600))
         self._multi = MultiStreamTrigger(model_dir, model_type, 1, max_chunk, pre_emphasis,
                                          posterior_threshold, device, precision)
