@@ -134,6 +134,7 @@ static int build_crnn(wwb_ctx* ctx, const wwb_weights* w) {
   // conv [32][100] -> [100][32]
   if ((rc = upload(ctx, transposed(w->conv_w, 32, 100), &C.conv_w))) return rc;
   if ((rc = upload(ctx, std::vector<float>(w->conv_b, w->conv_b + 32), &C.conv_b))) return rc;
+  if ((rc = upload(ctx, crnn_pack_conv(w->conv_w), &C.tc_conv))) return rc;
   for (int layer = 0; layer < 2; ++layer) {
     const int in = layer == 0 ? 640 : 64;
     // both directions side by side: Wt [in][192], bias [192]
@@ -152,6 +153,7 @@ static int build_crnn(wwb_ctx* ctx, const wwb_weights* w) {
       for (int dir = 0; dir < 2; ++dir)
         memcpy(&w_nk[(size_t)dir * 96 * in], w->gru_w[layer * 2 + dir], sizeof(float) * 96 * in);
       if ((rc = upload(ctx, pack_gemm_b(w_nk.data(), in, true), &C.gemm_b[layer]))) return rc;
+      if (layer == 0 && (rc = upload(ctx, crnn_pack_w1(w_nk.data()), &C.tc_w1))) return rc;
     }
     for (int dir = 0; dir < 2; ++dir) {
       if ((rc = upload(ctx, transposed(w->gru_u[layer * 2 + dir], 96, 32), &C.gru_u[layer * 2 + dir]))) return rc;

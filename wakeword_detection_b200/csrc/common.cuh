@@ -44,6 +44,8 @@ struct CrnnWeights {   // device copies, fp32, layouts chosen for the kernels
   float* det2_w = nullptr;   // [n_out][64]
   float* det2_b = nullptr;
   unsigned char* gemm_b[2] = {};   // tensor-core path: packed hi/lo fp16 weight stages (tc_gemm.cu), per layer
+  unsigned char* tc_conv = nullptr;   // crnn_tc.cu: packed conv weights
+  unsigned char* tc_w1 = nullptr;     // crnn_tc.cu: 20 packed k-slices of the layer-1 input projection
 };
 
 struct WavenetWeights {
@@ -170,6 +172,9 @@ int tc_gemm_bias(wwb_ctx* ctx, const float* A, const unsigned char* Bpacked, con
 int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
                          float* post, cudaStream_t st);
 int crnn_simt_detect(wwb_ctx* ctx, const float* enc, int64_t B, float* out, cudaStream_t st);
+std::vector<unsigned char> crnn_pack_conv(const float* conv_w);
+std::vector<unsigned char> crnn_pack_w1(const float* w_nk);
+int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st);
 int wavenet_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
                             float* post, cudaStream_t st);
 int wavenet_tc_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,

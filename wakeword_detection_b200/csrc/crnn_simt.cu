@@ -226,15 +226,15 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
     sub.n_win = nb;
     sub.b0 = wm.b0 + b0;
     float* enc = enc_out ? enc_out + b0 * 64 : (float*)enc_ws;
-    crnn_conv_kernel<<<(unsigned)nb, 256, 0, st>>>(sub, W.conv_w, W.conv_b, (float*)conv, ctx->L);
-    WWB_CHECK_LAUNCH(ctx);
     const int64_t M = nb * C_T;
     // both directions of a layer share one GEMM: Wt = [in][192]
     const bool tc = ctx->precision != WWB_PREC_F32;
     const int nsplit = ctx->precision == WWB_PREC_TC ? 3 : 1;
     if (tc) {
-      if ((rc = tc_gemm_bias(ctx, (float*)conv, W.gemm_b[0], W.gru_bi[0], (float*)xw, M, C_FEAT, nsplit, st))) return rc;
+      if ((rc = crnn_front_tc(ctx, sub, (float*)xw, st))) return rc;
     } else {
+      crnn_conv_kernel<<<(unsigned)nb, 256, 0, st>>>(sub, W.conv_w, W.conv_b, (float*)conv, ctx->L);
+      WWB_CHECK_LAUNCH(ctx);
       sgemm_bias_kernel<<<dim3((unsigned)((M + 63) / 64), 3), 256, 0, st>>>((float*)conv, W.gru_w[0], W.gru_bi[0],
                                                                             (float*)xw, M, 2 * C_G, C_FEAT);
       WWB_CHECK_LAUNCH(ctx);
