@@ -155,6 +155,18 @@ static int build_crnn(wwb_ctx* ctx, const wwb_weights* w) {
       if ((rc = upload(ctx, pack_gemm_b(w_nk.data(), in, true), &C.gemm_b[layer]))) return rc;
       if (layer == 0 && (rc = upload(ctx, crnn_pack_w1(w_nk.data()), &C.tc_w1))) return rc;
     }
+    {  // tensor-core recurrence: packed U, candidate-gate bias, input bias with the z/r recurrent bias folded in
+      if ((rc = upload(ctx, crnn_pack_u(w->gru_u[layer * 2], w->gru_u[layer * 2 + 1]), &C.tc_u[layer]))) return rc;
+      std::vector<float> bh(64), bf(192);
+      for (int dir = 0; dir < 2; ++dir)
+        for (int n = 0; n < 96; ++n) {
+          const float br = w->gru_br[layer * 2 + dir][n];
+          if (n >= 64) bh[dir * 32 + n - 64] = br;
+          bf[dir * 96 + n] = n < 64 ? bi[dir * 96 + n] + br : bi[dir * 96 + n];
+        }
+      if ((rc = upload(ctx, bh, &C.tc_bh[layer]))) return rc;
+      if ((rc = upload(ctx, bf, &C.tc_bi[layer]))) return rc;
+    }
     for (int dir = 0; dir < 2; ++dir) {
       if ((rc = upload(ctx, transposed(w->gru_u[layer * 2 + dir], 96, 32), &C.gru_u[layer * 2 + dir]))) return rc;
       if ((rc = upload(ctx, std::vector<float>(w->gru_br[layer * 2 + dir], w->gru_br[layer * 2 + dir] + 96),

@@ -46,6 +46,9 @@ struct CrnnWeights {   // device copies, fp32, layouts chosen for the kernels
   unsigned char* gemm_b[2] = {};   // tensor-core path: packed hi/lo fp16 weight stages (tc_gemm.cu), per layer
   unsigned char* tc_conv = nullptr;   // crnn_tc.cu: packed conv weights
   unsigned char* tc_w1 = nullptr;     // crnn_tc.cu: 20 packed k-slices of the layer-1 input projection
+  unsigned char* tc_u[2] = {};        // crnn_tc.cu: packed recurrent weights, both directions, per layer
+  float* tc_bh[2] = {};               // [2][32] recurrent bias of the candidate gate, per layer
+  float* tc_bi[2] = {};               // [192] b_in with the z/r parts of the recurrent bias folded in
 };
 
 struct WavenetWeights {
@@ -168,13 +171,16 @@ struct WinMap {
 
 std::vector<unsigned char> pack_gemm_b(const float* w_nk, int K, bool split);
 int tc_gemm_bias(wwb_ctx* ctx, const float* A, const unsigned char* Bpacked, const float* bias, float* C, int64_t M,
-                 int K, int nsplit, cudaStream_t st);
+                 int K, int nsplit, int xw_layout, cudaStream_t st);
 int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
                          float* post, cudaStream_t st);
 int crnn_simt_detect(wwb_ctx* ctx, const float* enc, int64_t B, float* out, cudaStream_t st);
 std::vector<unsigned char> crnn_pack_conv(const float* conv_w);
 std::vector<unsigned char> crnn_pack_w1(const float* w_nk);
 int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st);
+std::vector<unsigned char> crnn_pack_u(const float* u_f, const float* u_b);
+int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* last_out, int64_t B,
+               const int32_t* n_dev, cudaStream_t st);
 int wavenet_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
                             float* post, cudaStream_t st);
 int wavenet_tc_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,

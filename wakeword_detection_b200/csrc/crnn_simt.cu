@@ -212,11 +212,12 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
   if (B == 0) return WWB_OK;
   const CrnnWeights& W = ctx->crnn;
   // chunk the batch so the conv intermediate stays bounded (48.6 KB per window)
-  const int64_t chunk = 16384;
+  // a multiple of 128 windows x 2 CTAs x 148 SMs (the recurrence kernel's wave)
+  const int64_t chunk = 37888;
   void *conv, *xw, *s1, *enc_ws;
   int rc;
   if ((rc = workspace(ctx, 1, (size_t)std::min(B, chunk) * C_T * C_FEAT * 4, &conv))) return rc;
-  if ((rc = workspace(ctx, 2, (size_t)std::min(B, chunk) * C_T * 2 * C_G * 4, &xw))) return rc;
+  if ((rc = workspace(ctx, 2, (size_t)((std::min(B, chunk) + 127) / 128 * 128) * C_T * 2 * C_G * 4, &xw))) return rc;
   if ((rc = workspace(ctx, 3, (size_t)std::min(B, chunk) * C_T * 64 * 4, &s1))) return rc;
   if ((rc = workspace(ctx, 4, (size_t)std::min(B, chunk) * 64 * 4, &enc_ws))) return rc;
   if (wm.n_win_dev && B > chunk) return fail(ctx, WWB_ERR_ARG, "streaming batch too large");
@@ -239,19 +240,21 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
                                                                             (float*)xw, M, 2 * C_G, C_FEAT);
       WWB_CHECK_LAUNCH(ctx);
     }
-    gru_rec_kernel<<<(unsigned)((nb + 3) / 4), 256, 0, st>>>((float*)xw, W.gru_u[0], W.gru_br[0], W.gru_u[1],
-                                                            W.gru_br[1], (float*)s1, nullptr, nb, wm.n_win_dev);
-    WWB_CHECK_LAUNCH(ctx);
     if (tc) {
-      if ((rc = tc_gemm_bias(ctx, (float*)s1, W.gemm_b[1], W.gru_bi[2], (float*)xw, M, 64, nsplit, st))) return rc;
+      if ((rc = gru_rec_tc(ctx, 0, (float*)xw, (float*)s1, nullptr, nb, wm.n_win_dev, st))) return rc;
+      if ((rc = tc_gemm_bias(ctx, (float*)s1, W.gemm_b[1], W.tc_bi[1], (float*)xw, M, 64, nsplit, 1, st))) return rc;
+      if ((rc = gru_rec_tc(ctx, 1, (float*)xw, nullptr, enc, nb, wm.n_win_dev, st))) return rc;
     } else {
+      gru_rec_kernel<<<(unsigned)((nb + 3) / 4), 256, 0, st>>>((float*)xw, W.gru_u[0], W.gru_br[0], W.gru_u[1],
+                                                              W.gru_br[1], (float*)s1, nullptr, nb, wm.n_win_dev);
+      WWB_CHECK_LAUNCH(ctx);
       sgemm_bias_kernel<<<dim3((unsigned)((M + 63) / 64), 3), 256, 0, st>>>((float*)s1, W.gru_w[2], W.gru_bi[2],
                                                                             (float*)xw, M, 2 * C_G, 64);
       WWB_CHECK_LAUNCH(ctx);
+      gru_rec_kernel<<<(unsigned)((nb + 3) / 4), 256, 0, st>>>((float*)xw, W.gru_u[2], W.gru_br[2], W.gru_u[3],
+                                                              W.gru_br[3], nullptr, enc, nb, wm.n_win_dev);
+      WWB_CHECK_LAUNCH(ctx);
     }
-    gru_rec_kernel<<<(unsigned)((nb + 3) / 4), 256, 0, st>>>((float*)xw, W.gru_u[2], W.gru_br[2], W.gru_u[3],
-                                                            W.gru_br[3], nullptr, enc, nb, wm.n_win_dev);
-    WWB_CHECK_LAUNCH(ctx);
     if (det_out || post) {
       crnn_detect_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, st>>>(
           enc, W.det1_w, W.det1_b, W.det2_w, W.det2_b, ctx->n_out,

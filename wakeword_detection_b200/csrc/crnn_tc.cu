@@ -43,19 +43,20 @@ constexpr int CA_XP_PLANE = CA_RING_ROWS * CA_PITCH;
 constexpr int CA_GROUPS = 7;                      // 8-row groups per tile (padded rows p = freq + 8, 0..55)
 constexpr int CA_A1_PLANE = 4 * 128 * 16;         // one k-slice (32 values) of 128 rows
 constexpr int CA_W1_SLICE = 2 * 4 * 192 * 16;     // hi + lo planes of one k-slice of W1
-constexpr int CA_W1_SLOTS = 3;
+constexpr int CA_W1_SLOTS = 2;
+constexpr int CA_CR = 3;                          // conv accumulator / A1 slice ring depth
 constexpr int CA_CW_PLANE = 16 * 32 * 16;         // conv weights: 16 k-chunks x 32 channels
 constexpr int CA_EPI_WARPS = 4, CA_PROD_WARPS = 4;
 constexpr int CA_THREADS = (CA_EPI_WARPS + 2 + CA_PROD_WARPS) * 32;   // 320
 
 struct CaSmem {
   unsigned char xp[2 * CA_XP_PLANE];
-  unsigned char a1[2][2 * CA_A1_PLANE];
+  unsigned char a1[CA_CR][2 * CA_A1_PLANE];
   unsigned char w1[CA_W1_SLOTS][CA_W1_SLICE];
   unsigned char cw[2 * CA_CW_PLANE];
   float conv_b[32];
   float b_in[192];
-  uint64_t xp_full[3], xp_empty[3], cacc_full[2], cacc_empty[2], a1_full[2], a1_empty[2];
+  uint64_t xp_full[3], xp_empty[3], cacc_full[CA_CR], cacc_empty[CA_CR], a1_full[CA_CR], a1_empty[CA_CR];
   uint64_t w1_full[CA_W1_SLOTS], w1_empty[CA_W1_SLOTS], pacc_full[2], pacc_empty[2];
   uint32_t tmem_base;
 };
@@ -66,7 +67,7 @@ struct CaParams {
   const unsigned char* w1;      // [20][CA_W1_SLICE]
   const float* conv_b;
   const float* b_in;            // [192]
-  float* xw1;                   // [n_win, 19, 192]
+  float* xw1;                   // [ceil(n_win/128), 19, 48, 128] float4 (see the projection epilogue)
   int L;
   int nsplit;
 };
@@ -93,11 +94,11 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
   if (tid < 192) sm.b_in[tid] = P.b_in[tid];
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(&sm.xp_full[i], CA_PROD_WARPS); mbar_init(&sm.xp_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < CA_CR; ++i) {
       mbar_init(&sm.cacc_full[i], 1); mbar_init(&sm.cacc_empty[i], CA_EPI_WARPS);
       mbar_init(&sm.a1_full[i], CA_EPI_WARPS); mbar_init(&sm.a1_empty[i], 1);
-      mbar_init(&sm.pacc_full[i], 1); mbar_init(&sm.pacc_empty[i], CA_EPI_WARPS);
     }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.pacc_full[i], 1); mbar_init(&sm.pacc_empty[i], CA_EPI_WARPS); }
     for (int i = 0; i < CA_W1_SLOTS; ++i) { mbar_init(&sm.w1_full[i], 1); mbar_init(&sm.w1_empty[i], 1); }
     mbar_fence_init();
   }
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
-  const uint32_t TM_CACC = 0, TM_PACC = 64;   // conv acc: 2 x 32 cols; projection acc: 2 x 192 cols
+  const uint32_t TM_CACC = 0, TM_PACC = 128;   // conv acc ring: 3 x 32 cols; projection acc: 2 x 192 cols
 
   if (warp < CA_EPI_WARPS) {
     // =========================== epilogue warps: one row each ===========================
@@ -121,8 +122,9 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
       const bool valid = (wl < CA_WPT) && (t < CA_T) && (b < n_win);
       for (int f = 0; f < CA_F; ++f) {
         const uint32_t ci = tcount * CA_F + f;
-        const int cb = ci & 1;
-        mbar_wait(&sm.cacc_full[cb], (ci >> 1) & 1);
+        const int cb = ci % CA_CR;
+        const uint32_t cph = (ci / CA_CR) & 1;
+        mbar_wait(&sm.cacc_full[cb], cph);
         fence_after_sync();
         float v0[16], v1[16];
         tmem_ld16(tlane + TM_CACC + cb * 32, v0);
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
           }
           split8v(x, hi[c], lo[c]);
         }
-        mbar_wait(&sm.a1_empty[cb], ((ci >> 1) & 1) ^ 1);
+        mbar_wait(&sm.a1_empty[cb], cph ^ 1);
         unsigned char* a1 = sm.a1[cb] + r * 16;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -157,7 +159,9 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
       const int pb = tcount & 1;
       mbar_wait(&sm.pacc_full[pb], (tcount >> 1) & 1);
       fence_after_sync();
-      float* dst = P.xw1 + (b * CA_T + t) * 192;
+      // xw layout: [tile of 128 windows][t][48 float4 columns][128 windows] so that the recurrence
+      // kernel (one thread per window) reads it fully coalesced
+      float4* dst = reinterpret_cast<float4*>(P.xw1) + (((b >> 7) * CA_T + t) * 48) * 128 + (b & 127);
 #pragma unroll 1
       for (int c0 = 0; c0 < 192; c0 += 16) {
         float v[16];
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         if (valid) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            reinterpret_cast<float4*>(dst + c0)[i] =
+            dst[(c0 / 4 + i) * 128] =
                 make_float4(v[4 * i] + sm.b_in[c0 + 4 * i], v[4 * i + 1] + sm.b_in[c0 + 4 * i + 1],
                             v[4 * i + 2] + sm.b_in[c0 + 4 * i + 2], v[4 * i + 3] + sm.b_in[c0 + 4 * i + 3]);
         }
@@ -182,9 +186,9 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
     const int nsplit = P.nsplit;
     uint32_t tcount = 0, w1cnt = 0;
     auto inproj = [&](uint32_t ci, int f, uint32_t pacc) {
-      const int cb = ci & 1;
+      const int cb = ci % CA_CR;
       const int sl = w1cnt % CA_W1_SLOTS;
-      mbar_wait(&sm.a1_full[cb], (ci >> 1) & 1);
+      mbar_wait(&sm.a1_full[cb], (ci / CA_CR) & 1);
       mbar_wait(&sm.w1_full[sl], (w1cnt / CA_W1_SLOTS) & 1);
       fence_after_sync();
       const uint32_t a_hi = smem_u32(sm.a1[cb]), a_lo = a_hi + CA_A1_PLANE;
@@ -213,13 +217,13 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
       int groups_ready = 0;
       for (int f = 0; f < CA_F; ++f) {
         const uint32_t ci = tcount * CA_F + f;
-        const int cb = ci & 1;
+        const int cb = ci % CA_CR;
         const int g_hi = (2 * f + 12) >> 3;
         for (; groups_ready <= g_hi; ++groups_ready) {
           const uint32_t gg = gbase + groups_ready;
           mbar_wait(&sm.xp_full[gg % 3], (gg / 3) & 1);
         }
-        mbar_wait(&sm.cacc_empty[cb], ((ci >> 1) & 1) ^ 1);
+        mbar_wait(&sm.cacc_empty[cb], ((ci / CA_CR) & 1) ^ 1);
         fence_after_sync();
         const uint32_t cacc = tmem + TM_CACC + cb * 32;
 #pragma unroll
@@ -244,13 +248,15 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
           if (f == CA_F - 1) { mma_commit(&sm.xp_empty[(gbase + 5) % 3]); mma_commit(&sm.xp_empty[(gbase + 6) % 3]); }
         }
         __syncwarp();
-        if (f == 0) {
+        // the projection runs two slices behind the conv so that the epilogue of a slice has a
+        // whole conv + projection period to turn the accumulator into the next A operand
+        if (f == 1) {
           mbar_wait(&sm.pacc_empty[pb], ((tcount >> 1) & 1) ^ 1);
           fence_after_sync();
-        } else {
-          inproj(ci - 1, f - 1, pacc);
         }
+        if (f >= 2) inproj(ci - 2, f - 2, pacc);
       }
+      inproj(tcount * CA_F + CA_F - 2, CA_F - 2, pacc);
       inproj(tcount * CA_F + CA_F - 1, CA_F - 1, pacc);
       if (elect_one()) mma_commit(&sm.pacc_full[pb]);
       __syncwarp();
@@ -368,7 +374,7 @@ int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st) {
   P.cw = ctx->crnn.tc_conv;
   P.w1 = ctx->crnn.tc_w1;
   P.conv_b = ctx->crnn.conv_b;
-  P.b_in = ctx->crnn.gru_bi[0];
+  P.b_in = ctx->crnn.tc_bi[0];
   P.xw1 = xw1;
   P.L = ctx->L;
   P.nsplit = ctx->precision == WWB_PREC_TC ? 3 : 1;
@@ -377,6 +383,244 @@ int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st) {
   const int64_t n_tiles = (wm.n_win + CA_WPT - 1) / CA_WPT;
   const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, ctx->sm_count);
   crnn_front_tc_kernel<<<grid, CA_THREADS, smem, st>>>(P);
+  WWB_CHECK_LAUNCH(ctx);
+  return WWB_OK;
+}
+
+}  // namespace wwb
+
+// ---------------------------------------------------------------------------------------------
+// K3 (recurrence) — one bidirectional GRU layer (Keras v2, reset_after, gates z|r|h; the four
+// WHILE bodies of CRNN/encode.tflite) for 128 windows per CTA with the
+// windows on the M axis of the tensor core:
+//     per step   D_dir[128, 96] = h_dir[128, 32] . U_dir^T          (tcgen05, fp16 hi/lo split)
+//                z = sig(xz + hz), r = sig(xr + hr), c = tanh(xh + r*(hh + b_h)), h = c + z*(h - c)
+// xw (the input projection incl. b_in and the z/r parts of the recurrent bias) comes from global
+// memory, one 384-byte row per (window, t, dir).  Warps 0-3 run the forward direction (t = s),
+// warps 4-7 the backward one (t = 18 - s); each thread owns one window: its h[32] stays in
+// registers, the fp16-split copy in shared memory is the A operand of the next step.
+namespace wwb {
+
+using namespace tc;
+
+constexpr int GR_T = 19;
+constexpr int GR_H_BYTES = 2 * 4 * 128 * 16;     // hi + lo planes, K = 32
+constexpr int GR_U_BYTES = 2 * 4 * 96 * 16;
+constexpr int GR_THREADS = 9 * 32;
+
+struct GrSmem {
+  unsigned char h[2][GR_H_BYTES];
+  unsigned char u[2][GR_U_BYTES];
+  float bh[2][32];
+  uint64_t acc_full[2], h_ready[2];
+  uint32_t tmem_base;
+};
+
+struct GrParams {
+  const float* xw;              // [ceil(B/128), 19, 48, 128] float4
+  const unsigned char* u;       // [2][GR_U_BYTES] packed
+  const float* bh;              // [2][32]  recurrent bias of the candidate gate
+  float* seq_out;               // [B, 19, 64] or null
+  float* last_out;              // [B, 64] or null
+  int64_t n_win;
+  const int32_t* n_win_dev;
+  int nsplit;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcpf(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float v) { return rcpf(1.f + ex2f(-1.4426950408889634f * v)); }
+// tanh(v) = 1 - 2/(1 + e^(2v)); e^(2v) = inf gives exactly 1, 0 gives exactly -1
+__device__ __forceinline__ float tanh_fast(float v) { return fmaf(-2.f, rcpf(1.f + ex2f(2.8853900817779268f * v)), 1.f); }
+
+__device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(GR_THREADS, 2) gru_rec_tc_kernel(const GrParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  GrSmem& sm = *reinterpret_cast<GrSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_win = P.n_win_dev ? (int64_t)*P.n_win_dev : P.n_win;
+  const int64_t n_tiles = (n_win + 127) / 128;
+
+  for (int i = tid; i < (int)(2 * GR_U_BYTES / 16); i += GR_THREADS)
+    reinterpret_cast<uint4*>(&sm.u[0][0])[i] = reinterpret_cast<const uint4*>(P.u)[i];
+  if (tid < 64) (&sm.bh[0][0])[tid] = P.bh[tid];
+  if (tid == 0) {
+    for (int d = 0; d < 2; ++d) { mbar_init(&sm.acc_full[d], 1); mbar_init(&sm.h_ready[d], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(&sm.tmem_base, 256);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp < 8) {
+    const int d = warp >> 2, q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + d * 96;
+    unsigned char* hrow = sm.h[d] + r * 16;
+    const float* bh = sm.bh[d];
+    uint32_t n_acc = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t b = tile * 128 + r;
+      const bool valid = b < n_win;
+      float h[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) h[i] = 0.f;
+      for (int s = 0; s < GR_T; ++s) {
+        const int t = d ? GR_T - 1 - s : s;
+        const float4* xp = reinterpret_cast<const float4*>(P.xw) + ((tile * GR_T + t) * 48 + d * 24) * 128 + r;
+        float4 xn[6];   // z, r, h parts of the next 8-unit chunk
+        xn[0] = __ldg(xp + 0 * 128); xn[1] = __ldg(xp + 1 * 128);
+        xn[2] = __ldg(xp + 8 * 128); xn[3] = __ldg(xp + 9 * 128);
+        xn[4] = __ldg(xp + 16 * 128); xn[5] = __ldg(xp + 17 * 128);
+        if (s > 0) {
+          mbar_wait(&sm.acc_full[d], n_acc & 1);
+          ++n_acc;
+          fence_after_sync();
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float4 xc[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) xc[i] = xn[i];
+          if (u < 3) {
+            xn[0] = __ldg(xp + (2 * u + 2) * 128); xn[1] = __ldg(xp + (2 * u + 3) * 128);
+            xn[2] = __ldg(xp + (2 * u + 10) * 128); xn[3] = __ldg(xp + (2 * u + 11) * 128);
+            xn[4] = __ldg(xp + (2 * u + 18) * 128); xn[5] = __ldg(xp + (2 * u + 19) * 128);
+          }
+          float hz[8], hr[8], hh[8];
+          if (s > 0) {
+            tmem_ld8f(tbase + u * 8, hz);
+            tmem_ld8f(tbase + 32 + u * 8, hr);
+            tmem_ld8f(tbase + 64 + u * 8, hh);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { hz[i] = 0.f; hr[i] = 0.f; hh[i] = 0.f; }
+          }
+          const float xz[8] = {xc[0].x, xc[0].y, xc[0].z, xc[0].w, xc[1].x, xc[1].y, xc[1].z, xc[1].w};
+          const float xr[8] = {xc[2].x, xc[2].y, xc[2].z, xc[2].w, xc[3].x, xc[3].y, xc[3].z, xc[3].w};
+          const float xh[8] = {xc[4].x, xc[4].y, xc[4].z, xc[4].w, xc[5].x, xc[5].y, xc[5].z, xc[5].w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float z = sigmoid_fast(xz[i] + hz[i]);
+            const float rr = sigmoid_fast(xr[i] + hr[i]);
+            const float c = tanh_fast(fmaf(rr, hh[i] + bh[u * 8 + i], xh[i]));
+            h[u * 8 + i] = fmaf(z, h[u * 8 + i] - c, c);
+          }
+        }
+        if (s < GR_T - 1) {
+          fence_before_sync();
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = h[c4 * 8 + i];
+            uint4 hi, lo;
+            split8v(x, hi, lo);
+            *reinterpret_cast<uint4*>(hrow + c4 * 2048) = hi;
+            *reinterpret_cast<uint4*>(hrow + GR_H_BYTES / 2 + c4 * 2048) = lo;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.h_ready[d]);
+        }
+        if (valid && P.seq_out) {
+          float4* dst = reinterpret_cast<float4*>(P.seq_out + (b * GR_T + t) * 64 + d * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+        }
+      }
+      if (valid && P.last_out) {
+        float4* dst = reinterpret_cast<float4*>(P.last_out + b * 64 + d * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+      }
+    }
+  } else {
+    // MMA issuer
+    const uint32_t idesc = make_idesc_f16(128, 96);
+    const int nsplit = P.nsplit;
+    uint32_t n_h = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int s = 1; s < GR_T; ++s, ++n_h) {
+        for (int d = 0; d < 2; ++d) {
+          mbar_wait(&sm.h_ready[d], n_h & 1);
+          fence_after_sync();
+          const uint32_t a_hi = smem_u32(sm.h[d]), a_lo = a_hi + GR_H_BYTES / 2;
+          const uint32_t b_hi = smem_u32(sm.u[d]), b_lo = b_hi + GR_U_BYTES / 2;
+          const uint32_t acc = tmem + d * 96;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint64_t dah = make_desc(a_hi + kk * 4096, 2048, 128), dal = make_desc(a_lo + kk * 4096, 2048, 128);
+            const uint64_t dbh = make_desc(b_hi + kk * 3072, 1536, 128), dbl = make_desc(b_lo + kk * 3072, 1536, 128);
+            mma_f16_ss_w(acc, dah, dbh, idesc, kk != 0);
+            if (nsplit == 3) {
+              mma_f16_ss_w(acc, dal, dbh, idesc, true);
+              mma_f16_ss_w(acc, dah, dbl, idesc, true);
+            }
+          }
+          if (elect_one()) mma_commit(&sm.acc_full[d]);
+          __syncwarp();
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 256);
+}
+
+// U [96][32] (gate-major rows z|r|h) -> [plane][4 chunks][96][8 halves]
+std::vector<unsigned char> crnn_pack_u(const float* u_f, const float* u_b) {
+  std::vector<unsigned char> out(2 * GR_U_BYTES, 0);
+  for (int d = 0; d < 2; ++d) {
+    const float* u = d ? u_b : u_f;
+    for (int c = 0; c < 4; ++c)
+      for (int n = 0; n < 96; ++n)
+        for (int e = 0; e < 8; ++e) {
+          const size_t off = (size_t)d * GR_U_BYTES + ((size_t)c * 96 + n) * 16 + e * 2;
+          put_split16(out, off, off + GR_U_BYTES / 2, u[n * 32 + c * 8 + e]);
+        }
+  }
+  return out;
+}
+
+int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* last_out, int64_t B,
+               const int32_t* n_dev, cudaStream_t st) {
+  if (B == 0) return WWB_OK;
+  GrParams P;
+  P.xw = xw;
+  P.u = ctx->crnn.tc_u[layer];
+  P.bh = ctx->crnn.tc_bh[layer];
+  P.seq_out = seq_out;
+  P.last_out = last_out;
+  P.n_win = B;
+  P.n_win_dev = n_dev;
+  P.nsplit = ctx->precision == WWB_PREC_TC ? 3 : 1;
+  const size_t smem = sizeof(GrSmem) + 128;
+  WWB_CUDA(ctx, cudaFuncSetAttribute(gru_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n_tiles = (B + 127) / 128;
+  const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 2 * (int64_t)ctx->sm_count);
+  gru_rec_tc_kernel<<<grid, GR_THREADS, smem, st>>>(P);
   WWB_CHECK_LAUNCH(ctx);
   return WWB_OK;
 }

@@ -38,7 +38,8 @@ struct GemmSmem {
 
 __global__ void __launch_bounds__(G_THREADS, 1)
 tc_gemm_bias_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bpacked,
-                    const float* __restrict__ bias, float* __restrict__ C, int64_t M, int K, int nsplit) {
+                    const float* __restrict__ bias, float* __restrict__ C, int64_t M, int K, int nsplit,
+                    int xw_layout) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -160,11 +161,17 @@ tc_gemm_bias_kernel(const float* __restrict__ A, const unsigned char* __restrict
         tmem_ld16(taddr + c0, v);
         tmem_ld_wait();
         if (grow < M) {
-          float4* dst = reinterpret_cast<float4*>(C + grow * G_N + c0);
+          // xw_layout: rows are (window b, t) pairs and the output goes to the coalesced layout of the
+          // recurrence kernel, [b / 128][t][48 float4 columns][b % 128] (crnn_tc.cu)
+          const int64_t b = grow / 19;
+          const int t = (int)(grow - b * 19);
+          float4* dst = xw_layout ? reinterpret_cast<float4*>(C) + (((b >> 7) * 19 + t) * 48 + c0 / 4) * 128 + (b & 127)
+                                  : reinterpret_cast<float4*>(C + grow * G_N + c0);
+          const int64_t step = xw_layout ? 128 : 1;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            dst[i] = make_float4(v[4 * i] + __ldg(bias + c0 + 4 * i), v[4 * i + 1] + __ldg(bias + c0 + 4 * i + 1),
-                                 v[4 * i + 2] + __ldg(bias + c0 + 4 * i + 2), v[4 * i + 3] + __ldg(bias + c0 + 4 * i + 3));
+            dst[i * step] = make_float4(v[4 * i] + __ldg(bias + c0 + 4 * i), v[4 * i + 1] + __ldg(bias + c0 + 4 * i + 1),
+                                        v[4 * i + 2] + __ldg(bias + c0 + 4 * i + 2), v[4 * i + 3] + __ldg(bias + c0 + 4 * i + 3));
         }
       }
       fence_before_sync();
@@ -196,14 +203,14 @@ std::vector<unsigned char> pack_gemm_b(const float* w_nk, int K, bool split) {
 }
 
 int tc_gemm_bias(wwb_ctx* ctx, const float* A, const unsigned char* Bpacked, const float* bias, float* C, int64_t M,
-                 int K, int nsplit, cudaStream_t st) {
+                 int K, int nsplit, int xw_layout, cudaStream_t st) {
   if (M == 0) return WWB_OK;
   if (K % G_KS) return fail(ctx, WWB_ERR_ARG, "tc_gemm: K must be a multiple of %d", G_KS);
   const size_t smem = sizeof(GemmSmem) + 128;
   WWB_CUDA(ctx, cudaFuncSetAttribute(tc_gemm_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (M + 127) / 128;
   const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, ctx->sm_count);
-  tc_gemm_bias_kernel<<<grid, G_THREADS, smem, st>>>(A, Bpacked, bias, C, M, K, nsplit);
+  tc_gemm_bias_kernel<<<grid, G_THREADS, smem, st>>>(A, Bpacked, bias, C, M, K, nsplit, xw_layout);
   WWB_CHECK_LAUNCH(ctx);
   return WWB_OK;
 }
