@@ -46,8 +46,8 @@ constexpr int CA_W1_SLICE = 2 * 4 * 192 * 16;     // hi + lo planes of one k-sli
 constexpr int CA_W1_SLOTS = 2;
 constexpr int CA_CR = 3;                          // conv accumulator / A1 slice ring depth
 constexpr int CA_CW_PLANE = 16 * 32 * 16;         // conv weights: 16 k-chunks x 32 channels
-constexpr int CA_EPI_WARPS = 4, CA_PROD_WARPS = 4;
-constexpr int CA_THREADS = (CA_EPI_WARPS + 2 + CA_PROD_WARPS) * 32;   // 320
+constexpr int CA_EPI_WARPS = 4, CA_PROD_WARPS = 4;                  // producer warps per set; two sets alternate groups
+constexpr int CA_THREADS = (CA_EPI_WARPS + 2 + 2 * CA_PROD_WARPS) * 32;   // 448
 
 struct CaSmem {
   unsigned char xp[2 * CA_XP_PLANE];
@@ -70,7 +70,10 @@ struct CaParams {
   float* xw1;                   // [ceil(n_win/128), 19, 48, 128] float4 (see the projection epilogue)
   int L;
   int nsplit;
+  long long* dbg;               // optional issuer timeline of the CTA's second tile: [20 f][8 events]
 };
+
+#define CA_DBG(f, ev) do { if (P.dbg && blockIdx.x == 0 && tcount == 1 && lane == 0) P.dbg[(f) * 8 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ void split8v(const float (&x)[8], uint4& hi, uint4& lo) {
   split_pair(x[0], x[1], hi.x, lo.x);
@@ -82,7 +85,8 @@ __device__ __forceinline__ void split8v(const float (&x)[8], uint4& hi, uint4& l
 __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   CaSmem& sm = *reinterpret_cast<CaSmem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role branches are uniform branches
   const int64_t n_win = P.wm.n_win_dev ? (int64_t)*P.wm.n_win_dev : P.wm.n_win;
   const int64_t n_tiles = (n_win + CA_WPT - 1) / CA_WPT;
 
@@ -117,6 +121,26 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
     const int wl = r / CA_TP, t = r - wl * CA_TP;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t tcount = 0;
+    // Projection epilogue (+ b_in -> xw1), 16 columns at a time.  It is DEFERRED: the accumulator of
+    // tile n is drained in 12 pieces during the first 12 conv steps of tile n+1 (the projection
+    // accumulator is double-buffered), because its 48 scattered 16-byte stores per row would
+    // otherwise stall the conv epilogue — and with it the tensor pipe — for ~10k cycles per tile.
+    // xw layout: [tile of 128 windows][t][48 float4 columns][128 windows]: the recurrence kernel
+    // (one thread per window) reads it fully coalesced.
+    auto proj_chunk = [&](int64_t pb_b, bool pvalid, int pbuf, int c0) {
+      float v[16];
+      tmem_ld16(tlane + TM_PACC + pbuf * 192 + c0, v);
+      tmem_ld_wait();
+      if (pvalid) {
+        float4* dst = reinterpret_cast<float4*>(P.xw1) + (((pb_b >> 7) * CA_T + t) * 48 + c0 / 4) * 128 + (pb_b & 127);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          dst[i * 128] = make_float4(v[4 * i] + sm.b_in[c0 + 4 * i], v[4 * i + 1] + sm.b_in[c0 + 4 * i + 1],
+                                     v[4 * i + 2] + sm.b_in[c0 + 4 * i + 2], v[4 * i + 3] + sm.b_in[c0 + 4 * i + 3]);
+      }
+    };
+    int64_t prev_b = 0;
+    bool prev_valid = false, have_prev = false;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const int64_t b = tile * CA_WPT + wl;
       const bool valid = (wl < CA_WPT) && (t < CA_T) && (b < n_win);
@@ -131,8 +155,6 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         tmem_ld16(tlane + TM_CACC + cb * 32 + 16, v1);
         tmem_ld_wait();
         fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.cacc_empty[cb]);
         uint4 hi[4], lo[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -154,33 +176,36 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.a1_full[cb]);
-      }
-      // ---- projection epilogue: + b_in -> xw1 ----
-      const int pb = tcount & 1;
-      mbar_wait(&sm.pacc_full[pb], (tcount >> 1) & 1);
-      fence_after_sync();
-      // xw layout: [tile of 128 windows][t][48 float4 columns][128 windows] so that the recurrence
-      // kernel (one thread per window) reads it fully coalesced
-      float4* dst = reinterpret_cast<float4*>(P.xw1) + (((b >> 7) * CA_T + t) * 48) * 128 + (b & 127);
-#pragma unroll 1
-      for (int c0 = 0; c0 < 192; c0 += 16) {
-        float v[16];
-        tmem_ld16(tlane + TM_PACC + pb * 192 + c0, v);
-        tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            dst[(c0 / 4 + i) * 128] =
-                make_float4(v[4 * i] + sm.b_in[c0 + 4 * i], v[4 * i + 1] + sm.b_in[c0 + 4 * i + 1],
-                            v[4 * i + 2] + sm.b_in[c0 + 4 * i + 2], v[4 * i + 3] + sm.b_in[c0 + 4 * i + 3]);
+        // one piece of the previous tile's projection accumulator
+        if (have_prev && f < 12) {
+          const uint32_t pt = tcount - 1;
+          if (f == 0) {
+            mbar_wait(&sm.pacc_full[pt & 1], (pt >> 1) & 1);
+            fence_after_sync();
+          }
+          proj_chunk(prev_b, prev_valid, pt & 1, f * 16);
+          if (f == 11) {
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.pacc_empty[pt & 1]);
+          }
         }
       }
+      prev_b = b; prev_valid = valid; have_prev = true;
+    }
+    if (have_prev) {   // drain the last tile
+      const uint32_t pt = tcount - 1;
+      mbar_wait(&sm.pacc_full[pt & 1], (pt >> 1) & 1);
+      fence_after_sync();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 192; c0 += 16) proj_chunk(prev_b, prev_valid, pt & 1, c0);
       fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.pacc_empty[pb]);
     }
   } else if (warp == CA_EPI_WARPS) {
     // =========================== MMA issuer ===========================
+    // All MMAs of one step are issued by ONE elected lane inside a single branch (descriptors are
+    // built there with integer adds); per-MMA election costs ~20 extra instructions on this warp,
+    // which made the issue rate, not the tensor pipe, the limiter (profiles/r1_crnn_front.md).
     const uint32_t idesc_c = make_idesc_f16(128, 32), idesc_p = make_idesc_f16(128, 192);
     const uint32_t uXP = smem_u32(sm.xp), uCW = smem_u32(sm.cw);
     const int nsplit = P.nsplit;
@@ -188,26 +213,30 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
     auto inproj = [&](uint32_t ci, int f, uint32_t pacc) {
       const int cb = ci % CA_CR;
       const int sl = w1cnt % CA_W1_SLOTS;
+      CA_DBG(f, 4);
       mbar_wait(&sm.a1_full[cb], (ci / CA_CR) & 1);
+      CA_DBG(f, 5);
       mbar_wait(&sm.w1_full[sl], (w1cnt / CA_W1_SLOTS) & 1);
+      CA_DBG(f, 6);
       fence_after_sync();
-      const uint32_t a_hi = smem_u32(sm.a1[cb]), a_lo = a_hi + CA_A1_PLANE;
-      const uint32_t b_hi = smem_u32(sm.w1[sl]), b_lo = b_hi + CA_W1_SLICE / 2;
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const uint64_t dah = make_desc(a_hi + kk * 4096, 2048, 128), dal = make_desc(a_lo + kk * 4096, 2048, 128);
-        const uint64_t dbh = make_desc(b_hi + kk * 6144, 3072, 128), dbl = make_desc(b_lo + kk * 6144, 3072, 128);
-        mma_f16_ss_w(pacc, dah, dbh, idesc_p, (f | kk) != 0);
-        if (nsplit == 3) {
-          mma_f16_ss_w(pacc, dal, dbh, idesc_p, true);
-          mma_f16_ss_w(pacc, dah, dbl, idesc_p, true);
-        }
-      }
       if (elect_one()) {
+        const uint64_t da = make_desc(smem_u32(sm.a1[cb]), 2048, 128);
+        const uint64_t db = make_desc(smem_u32(sm.w1[sl]), 3072, 128);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint64_t dah = da + (uint64_t)(kk * (4096 >> 4)), dal = dah + (uint64_t)(CA_A1_PLANE >> 4);
+          const uint64_t dbh = db + (uint64_t)(kk * (6144 >> 4)), dbl = dbh + (uint64_t)((CA_W1_SLICE / 2) >> 4);
+          mma_f16_ss(pacc, dah, dbh, idesc_p, (f | kk) != 0);
+          if (nsplit == 3) {
+            mma_f16_ss(pacc, dal, dbh, idesc_p, true);
+            mma_f16_ss(pacc, dah, dbl, idesc_p, true);
+          }
+        }
         mma_commit(&sm.a1_empty[cb]);
         mma_commit(&sm.w1_empty[sl]);
       }
       __syncwarp();
+      CA_DBG(f, 7);
       ++w1cnt;
     };
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
@@ -218,43 +247,52 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
       for (int f = 0; f < CA_F; ++f) {
         const uint32_t ci = tcount * CA_F + f;
         const int cb = ci % CA_CR;
+        // The projection runs two slices behind the conv, so the epilogue of a slice has a whole
+        // conv + projection period to turn the accumulator into the next A operand.  Waiting for
+        // a1_full(ci-2) here also proves that conv accumulator ci%3 (last used by slice ci-3, whose
+        // epilogue finished before that of ci-2) is free again.
+        if (f == 2) {
+          mbar_wait(&sm.pacc_empty[pb], ((tcount >> 1) & 1) ^ 1);
+          fence_after_sync();
+        }
+        if (f >= 2) inproj(ci - 2, f - 2, pacc);
         const int g_hi = (2 * f + 12) >> 3;
+        CA_DBG(f, 0);
         for (; groups_ready <= g_hi; ++groups_ready) {
           const uint32_t gg = gbase + groups_ready;
           mbar_wait(&sm.xp_full[gg % 3], (gg / 3) & 1);
         }
-        mbar_wait(&sm.cacc_empty[cb], ((ci / CA_CR) & 1) ^ 1);
+        CA_DBG(f, 1);
         fence_after_sync();
-        const uint32_t cacc = tmem + TM_CACC + cb * 32;
+        uint32_t rowaddr[5];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          const int q0 = 2 * m, kf0 = q0 / 3, j0 = q0 % 3;
-          const int rowp = 2 * f + 7 + kf0;
-          const uint32_t phys = ((gbase + (rowp >> 3)) % 3) * 8 + (rowp & 7);
-          const uint32_t lbo = (j0 == 2 && m != 7) ? (uint32_t)(CA_PITCH - 32) : 16u;
-          const uint32_t a0 = uXP + phys * CA_PITCH + j0 * 16;
-          const uint64_t dah = make_desc(a0, lbo, 128), dal = make_desc(a0 + CA_XP_PLANE, lbo, 128);
-          const uint64_t dbh = make_desc(uCW + q0 * 512, 512, 128), dbl = make_desc(uCW + CA_CW_PLANE + q0 * 512, 512, 128);
-          mma_f16_ss_w(cacc, dah, dbh, idesc_c, m != 0);
-          if (nsplit == 3) {
-            mma_f16_ss_w(cacc, dal, dbh, idesc_c, true);
-            mma_f16_ss_w(cacc, dah, dbl, idesc_c, true);
-          }
+        for (int kf = 0; kf < 5; ++kf) {
+          const int rowp = 2 * f + 7 + kf;
+          rowaddr[kf] = uXP + (((gbase + (rowp >> 3)) % 3) * 8 + (rowp & 7)) * CA_PITCH;
         }
+        CA_DBG(f, 2);
         if (elect_one()) {
+          const uint32_t cacc = tmem + TM_CACC + cb * 32;
+          const uint64_t dbase = make_desc(uCW, 512, 128);
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const int q0 = 2 * m, kf0 = q0 / 3, j0 = q0 % 3;
+            const uint32_t lbo = (j0 == 2 && m != 7) ? (uint32_t)(CA_PITCH - 32) : 16u;
+            const uint64_t dah = make_desc(rowaddr[kf0] + j0 * 16, lbo, 128), dal = dah + (uint64_t)(CA_XP_PLANE >> 4);
+            const uint64_t dbh = dbase + (uint64_t)((q0 * 512) >> 4), dbl = dbh + (uint64_t)(CA_CW_PLANE >> 4);
+            mma_f16_ss(cacc, dah, dbh, idesc_c, m != 0);
+            if (nsplit == 3) {
+              mma_f16_ss(cacc, dal, dbh, idesc_c, true);
+              mma_f16_ss(cacc, dah, dbl, idesc_c, true);
+            }
+          }
           mma_commit(&sm.cacc_full[cb]);
           // group f/4 was last read by conv(f) when f = 4*(f/4)
           if ((f & 3) == 0) mma_commit(&sm.xp_empty[(gbase + (f >> 2)) % 3]);
           if (f == CA_F - 1) { mma_commit(&sm.xp_empty[(gbase + 5) % 3]); mma_commit(&sm.xp_empty[(gbase + 6) % 3]); }
         }
         __syncwarp();
-        // the projection runs two slices behind the conv so that the epilogue of a slice has a
-        // whole conv + projection period to turn the accumulator into the next A operand
-        if (f == 1) {
-          mbar_wait(&sm.pacc_empty[pb], ((tcount >> 1) & 1) ^ 1);
-          fence_after_sync();
-        }
-        if (f >= 2) inproj(ci - 2, f - 2, pacc);
+        CA_DBG(f, 3);
       }
       inproj(tcount * CA_F + CA_F - 2, CA_F - 2, pacc);
       inproj(tcount * CA_F + CA_F - 1, CA_F - 1, pacc);
@@ -275,7 +313,8 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
     }
   } else {
     // =========================== XP producers ===========================
-    const int task = tid - (CA_EPI_WARPS + 2) * 32;      // 0..127; element e = task
+    const int pset = (warp - (CA_EPI_WARPS + 2)) / CA_PROD_WARPS;       // this set fills the groups with gg % 2 == pset
+    const int task = tid - (CA_EPI_WARPS + 2 + pset * CA_PROD_WARPS) * 32;   // 0..127; element e = task
     const int wl = task / CA_TP, c = task - wl * CA_TP;  // window in tile, time chunk (frames 8c-6 .. 8c+1)
     const bool has_task = task < CA_WPT * CA_TP;
     const int L = P.L;
@@ -284,6 +323,7 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
       const int64_t b = tile * CA_WPT + wl;
       const bool live = has_task && b < n_win;
       for (int g = 0; g < CA_GROUPS; ++g, ++gg) {
+        if ((int)(gg & 1) != pset) continue;
         const int slot = gg % 3;
         // issue the loads before waiting for the slot
         float4 v[8][2];
@@ -378,6 +418,7 @@ int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st) {
   P.xw1 = xw1;
   P.L = ctx->L;
   P.nsplit = ctx->precision == WWB_PREC_TC ? 3 : 1;
+  P.dbg = reinterpret_cast<long long*>(ctx->debug_buf);
   const size_t smem = sizeof(CaSmem) + 128;
   WWB_CUDA(ctx, cudaFuncSetAttribute(crnn_front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (wm.n_win + CA_WPT - 1) / CA_WPT;
@@ -453,7 +494,8 @@ __device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
 __global__ void __launch_bounds__(GR_THREADS, 2) gru_rec_tc_kernel(const GrParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GrSmem& sm = *reinterpret_cast<GrSmem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role branches are uniform branches
   const int64_t n_win = P.n_win_dev ? (int64_t)*P.n_win_dev : P.n_win;
   const int64_t n_tiles = (n_win + 127) / 128;
 
