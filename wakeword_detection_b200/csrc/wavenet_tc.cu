@@ -75,7 +75,7 @@ struct WnTcParams {
   long long* dbg;   // optional timeline dump (block 0, first group): [6 roles][24 blocks][4 events]
 };
 
-#define WN_DBG(role, k, ev) do { if (P.dbg && blockIdx.x == 0 && grp == 0) P.dbg[((role) * 24 + (k)) * 4 + (ev)] = clock64(); } while (0)
+#define WN_DBG(role, k, ev) do { if (P.dbg && blockIdx.x == 0 && grp == (int64_t)gridDim.x) P.dbg[((role) * 24 + (k)) * 4 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -127,7 +127,8 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WnSmem& sm = *reinterpret_cast<WnSmem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
   const int64_t n_win = P.wm.n_win_dev ? (int64_t)*P.wm.n_win_dev : P.wm.n_win;
   const int64_t n_groups = (n_win + WN_G - 1) / WN_G;
   const int L = P.L;
@@ -383,22 +384,23 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         for (int i = 0; i < WN_NT; ++i) {
           mbar_wait(&sm.bar_u[i], n_u & 1);
           fence_after_sync();
-          {
+          if (elect_one()) {   // one lane issues the whole tile (uniform descriptors, no per-MMA election)
             const uint32_t dst = tmem + i * WN_TMEM_TILE;
+            const uint64_t db = make_desc(wb, 512, 128);
 #pragma unroll
             for (int tap = 0; tap < 3; ++tap) {
               const uint32_t arow = (uint32_t)(16 + i * 128 - (2 - tap) * d) * 16;
-              const uint64_t ah = make_desc(uU + arow, WN_PU, 128), al = make_desc(uU + 2 * WN_PU + arow, WN_PU, 128);
-              const uint64_t bh = make_desc(wb + tap * 2 * 512, 512, 128), bl = make_desc(wb + 3072 + tap * 2 * 512, 512, 128);
-              mma_f16_ss_w(dst, ah, bh, idesc_gate, tap != 0);
+              const uint64_t ah = make_desc(uU + arow, WN_PU, 128), al = ah + (uint64_t)((2 * WN_PU) >> 4);
+              const uint64_t bh = db + (uint64_t)((tap * 2 * 512) >> 4), bl = bh + (uint64_t)(3072 >> 4);
+              mma_f16_ss(dst, ah, bh, idesc_gate, tap != 0);
               if (nsplit == 3) {
-                mma_f16_ss_w(dst, al, bh, idesc_gate, true);
-                mma_f16_ss_w(dst, ah, bl, idesc_gate, true);
+                mma_f16_ss(dst, al, bh, idesc_gate, true);
+                mma_f16_ss(dst, ah, bl, idesc_gate, true);
               }
             }
-            if (elect_one()) mma_commit(&sm.bar_gate[i]);
-            if (lane == 0 && i == 0) WN_DBG(5, k, 0);
-            if (lane == 0 && i == WN_NT - 1) WN_DBG(5, k, 1);
+            mma_commit(&sm.bar_gate[i]);
+            if (i == 0) WN_DBG(5, k, 0);
+            if (i == WN_NT - 1) WN_DBG(5, k, 1);
           }
           __syncwarp();
         }
@@ -415,19 +417,19 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         for (int i = 0; i < WN_NT; ++i) {
           mbar_wait(&sm.bar_g[i], n_g & 1);
           fence_after_sync();
-          {
+          if (elect_one()) {
             const uint32_t dst = tmem + i * WN_TMEM_TILE + 32;
             const uint32_t arow = (uint32_t)(i * 128) * 16;
-            const uint64_t ah = make_desc(uG + arow, WN_PG, 128), al = make_desc(uG + 2 * WN_PG + arow, WN_PG, 128);
-            const uint64_t bh = make_desc(wb + WN_GATE_B, 768, 128), bl = make_desc(wb + WN_GATE_B + 1536, 768, 128);
-            mma_f16_ss_w(dst, ah, bh, idesc_rs, false);
+            const uint64_t ah = make_desc(uG + arow, WN_PG, 128), al = ah + (uint64_t)((2 * WN_PG) >> 4);
+            const uint64_t bh = make_desc(wb + WN_GATE_B, 768, 128), bl = bh + (uint64_t)(1536 >> 4);
+            mma_f16_ss(dst, ah, bh, idesc_rs, false);
             if (nsplit == 3) {
-              mma_f16_ss_w(dst, al, bh, idesc_rs, true);
-              mma_f16_ss_w(dst, ah, bl, idesc_rs, true);
+              mma_f16_ss(dst, al, bh, idesc_rs, true);
+              mma_f16_ss(dst, ah, bl, idesc_rs, true);
             }
-            if (elect_one()) mma_commit(&sm.bar_rs[i]);
-            if (lane == 0 && i == 0) WN_DBG(5, k, 2);
-            if (lane == 0 && i == WN_NT - 1) WN_DBG(5, k, 3);
+            mma_commit(&sm.bar_rs[i]);
+            if (i == 0) WN_DBG(5, k, 2);
+            if (i == WN_NT - 1) WN_DBG(5, k, 3);
           }
           __syncwarp();
         }
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       for (int i = 0; i < WN_NT; ++i) {
         mbar_wait(&sm.bar_u[i], n_u & 1);
         fence_after_sync();
-        {
+        if (elect_one()) {
           const uint32_t dst = tmem + i * WN_TMEM_TILE;
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
@@ -445,13 +447,13 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             const uint32_t pl = kk == 0 ? WN_PG : WN_PU;
             const uint64_t ah = make_desc(abase, pl, 128), al = make_desc(abase + 2 * pl, pl, 128);
             const uint64_t bh = make_desc(hb + kk * 2 * 512, 512, 128), bl = make_desc(hb + 2048 + kk * 2 * 512, 512, 128);
-            mma_f16_ss_w(dst, ah, bh, idesc_gate, kk != 0);
+            mma_f16_ss(dst, ah, bh, idesc_gate, kk != 0);
             if (nsplit == 3) {
-              mma_f16_ss_w(dst, al, bh, idesc_gate, true);
-              mma_f16_ss_w(dst, ah, bl, idesc_gate, true);
+              mma_f16_ss(dst, al, bh, idesc_gate, true);
+              mma_f16_ss(dst, ah, bl, idesc_gate, true);
             }
           }
-          if (elect_one()) mma_commit(&sm.bar_gate[i]);
+          mma_commit(&sm.bar_gate[i]);
         }
         __syncwarp();
       }
