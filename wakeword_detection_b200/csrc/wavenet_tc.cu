@@ -4,17 +4,29 @@
 // (window w, time t) -> o = w*198 + t form the M dimension of every GEMM (5 tiles of 128
 // rows; the 16 rows after each window are the next window's causal zero padding).  Each of
 // the 640 epilogue threads owns ONE row for the whole 24-block stack: its 16-channel
-// residual stream and 32-channel skip sum never leave registers.  Per block:
-//   gate GEMM   D[128,32] = sum_tap U[rows - (2-tap)*d, 16] * Wg_tap      (tcgen05, TMEM)
-//               the dilated taps are row-shifted views of one shared-memory buffer: the
-//               operand layout is linear in the row index, so a tap is a start-address offset
-//   epilogue 1  g = tanh(.)*sigmoid(.) (ex2/rcp), fp16 hi/lo -> shared memory
-//   res/skip    D[128,48] = g[128,16] * [Wres | Wskip]                   (tcgen05, TMEM)
-//   epilogue 2  x += ReLU(res); skip += ReLU(.); u = BN_next(x) -> hi/lo -> shared memory
-// then the detect head (32->32 on the tensor core, 32->2, max over time, softmax).
+// residual stream and 32-channel skip sum never leave registers.  Per block and tile:
+//   gate GEMM   D[128,32] = sum_tap U[rows - (2-tap)*d, 16] * Wg_tap          (tcgen05, TMEM)
+//               taps 0/1 (row-shifted) read A from shared memory: the operand layout is linear
+//               in the row index, so a dilated tap is a start-address offset;
+//               tap 2 (no shift) reads A straight from TENSOR MEMORY, where the row's owner
+//               thread stored it (tcgen05.st): 15.5 clk per MMA instead of 39.4 (tools/tc_rate_probe.cu)
+//   epilogue 1  g = tanh(.)*sigmoid(.) (ex2/rcp), fp16 hi/lo -> TMEM (A operand of the next GEMM)
+//   res/skip    D[128,48] = g[128,16] * [Wres | Wskip]       (A from TMEM, accumulator shared with the gate)
+//   epilogue 2  x += ReLU(res); skip += ReLU(.); u = BN_next(x) -> hi/lo -> shared memory + TMEM
+// then the detect head (32->32 on the tensor core, A from TMEM; 32->2, max over time, softmax).
+// Biases are added by the tensor core too: one extra k-step whose A chunk is the constant (1, 1, 0, ...)
+// and whose B rows hold (bias_hi, bias_lo, 0, ...) - broadcast loads of per-block constants from shared
+// memory cost one wavefront per 4 bytes and were the largest shared-memory consumer (profiles/).
+// The gate weights and biases are pre-scaled by -2*log2(e) (tanh half) / -log2(e) (sigmoid half).
 // fp16 hi/lo operand split (3 MMAs per product) keeps the result at fp32 accuracy
-// (DESIGN.md §precision).  Per-block weights (9.5 KB) stream through a 2-stage
-// cp.async.bulk ring; tiles of a block are pipelined through per-tile mbarriers.
+// (DESIGN.md §precision).  Epilogue arithmetic uses the packed fp32x2 instructions (FFMA2/FADD2).
+// Per-block weights (9.5 KB) stream through a 4-stage cp.async.bulk ring.
+//
+// The MMA warp issues in a static software-pipelined order (see the issuer) so that tiles run staggered:
+// the tensor pipe, the SFU and the FMA/ALU pipes are busy with different tiles at the same time.
+//   gate(k,i) needs epilogue 2 of (k-1,i) and (k-1,i-1)      (its taps reach 16 rows into tile i-1)
+//   rs(k,i)   needs epilogue 1 of (k,i) and gate(k,i+1) ISSUED: epilogue 2 of (k,i) overwrites rows
+//             gate(k,i+1) reads, and tcgen05 ops of one thread complete in order.
 #include <string.h>
 
 #include "common.cuh"
@@ -30,14 +42,19 @@ constexpr int WN_NT = 5;                      // M tiles per group
 constexpr int WN_ROWS = WN_NT * 128;          // 640
 constexpr int WN_UROWS = WN_ROWS + 16;        // U buffer has 16 leading zero rows
 constexpr int WN_PU = WN_UROWS * 16;          // bytes per U chunk panel
-constexpr int WN_PG = WN_ROWS * 16;           // bytes per G chunk panel
 constexpr int WN_EPI_WARPS = WN_NT * 4;       // 20
 constexpr int WN_EPI_THREADS = WN_EPI_WARPS * 32;
 constexpr int WN_THREADS = (WN_EPI_WARPS + 1) * 32;   // + MMA/loader warp = 672 (leaves 96 registers per thread)
-constexpr int WN_WBLK = 9728;                 // bytes of one block's weight blob
-constexpr int WN_GATE_B = 6144, WN_RS_B = 3072;
+constexpr int WN_GATE_B = 6144, WN_RS_B = 3072;   // gate / res+skip B operands (hi and lo planes)
+constexpr int WN_F32_B = 512;                     // fp32 constants: [80..95] next block's BN scale, [96..111] BN shift
+constexpr int WN_GBIAS_B = 1024, WN_RBIAS_B = 1536;   // bias B operands for the 'ones' GEMM (k0 = hi, k1 = lo)
+constexpr int WN_OFF_F32 = WN_GATE_B + WN_RS_B, WN_OFF_GBIAS = WN_OFF_F32 + WN_F32_B, WN_OFF_RBIAS = WN_OFF_GBIAS + WN_GBIAS_B;
+constexpr int WN_WBLK = WN_OFF_RBIAS + WN_RBIAS_B;    // 12288 bytes of one block's weight blob
 constexpr int WN_WST = 4;                     // weight ring stages
-constexpr int WN_TMEM_TILE = 96;              // columns per tile: gate 32 @0, res/skip 48 @32
+constexpr int WN_TMEM_TILE = 96;              // TMEM columns per tile:
+constexpr int WN_C_U = 48;                    //   accumulator 0..47 (gate 0..31, then res/skip 0..47),
+constexpr int WN_C_G = 64;                    //   u hi/lo 48..63, g hi/lo 64..79,
+constexpr int WN_C_ONE = 80;                  //   constant A chunk (k0 = k1 = 1, rest 0) 80..87: adds the biases on the tensor core
 
 // resident head blob (floats unless noted)
 struct WnHead {
@@ -53,7 +70,6 @@ struct WnHead {
 
 struct WnSmem {
   unsigned char U[2 * 2 * WN_PU];          // [plane][chunk][row]
-  unsigned char Gb[2 * 2 * WN_PG];
   unsigned char W[WN_WST][WN_WBLK];
   WnHead head;
   uint64_t bar_u[WN_NT], bar_gate[WN_NT], bar_g[WN_NT], bar_rs[WN_NT];
@@ -72,10 +88,12 @@ struct WnTcParams {
   float* enc_out;
   float* det_out;
   float* post;
-  long long* dbg;   // optional timeline dump (block 0, first group): [6 roles][24 blocks][4 events]
+  long long* dbg;   // optional timeline dump (block 0, second group): [8 roles][24 blocks][4 events]
 };
 
 #define WN_DBG(role, k, ev) do { if (P.dbg && blockIdx.x == 0 && grp == (int64_t)gridDim.x) P.dbg[((role) * 24 + (k)) * 4 + (ev)] = clock64(); } while (0)
+
+typedef unsigned long long u64;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -87,13 +105,26 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// tanh(a) * sigmoid(b) with two ex2 and one rcp
-// `a2` = -2*log2(e)*a and `b2` = -log2(e)*b arrive pre-scaled (bias folded in by an FFMA).
-// Only e^(-2a) can make the quotient inf/inf, so only it is clamped (tanh is +-1 to 1e-13 there).
-__device__ __forceinline__ float gate_fn(float a2, float b2) {
-  const float ea = ex2_approx(fminf(a2, 43.f));   // e^(-2a), a >= -14.9
-  const float eb = ex2_approx(b2);                // e^(-b); inf -> rcp(inf) = 0 -> g = 0
-  return (1.f - ea) * rcp_approx((1.f + ea) * (1.f + eb));
+// packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2): one issue slot for two lanes of work
+__device__ __forceinline__ u64 pk(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fsub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 relu2(u64 v) { float a, b; upk(v, a, b); return pk(fmaxf(a, 0.f), fmaxf(b, 0.f)); }
+
+// split a pair into fp16 hi (mantissa truncated to 10 bits) and fp16 lo (= x - hi, exact in fp32)
+__device__ __forceinline__ void split2(u64 v, uint32_t& hi, uint32_t& lo) {
+  float a, b;
+  upk(v, a, b);
+  const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+  const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  float la, lb;
+  upk(fsub2(v, pk(ah, bh)), la, lb);
+  __half2 h = __floats2half2_rn(ah, bh);
+  __half2 l = __floats2half2_rn(la, lb);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
@@ -104,14 +135,29 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-
-// 8 fp32 -> one 16-byte chunk of hi halves and one of lo halves
-__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
-  split_pair(x[0], x[1], hi.x, lo.x);
-  split_pair(x[2], x[3], hi.y, lo.y);
-  split_pair(x[4], x[5], hi.z, lo.z);
-  split_pair(x[6], x[7], hi.w, lo.w);
+// 16 consecutive columns of this thread's TMEM lane: an fp16 A operand chunk pair (hi 8 columns, lo 8 columns)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
 }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : A is 128 lanes x 8 columns (16 fp16 per lane)
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 __device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -135,7 +181,6 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
 
   // ---- one-time setup ----
   for (int i = tid; i < (int)(sizeof(sm.U) / 16); i += WN_THREADS) reinterpret_cast<uint4*>(sm.U)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < (int)(sizeof(sm.Gb) / 16); i += WN_THREADS) reinterpret_cast<uint4*>(sm.Gb)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < (int)(sizeof(WnHead) / 16); i += WN_THREADS)
     reinterpret_cast<uint4*>(&sm.head)[i] = reinterpret_cast<const uint4*>(P.head)[i];
   if (tid < WN_G * 2) sm.zmax[tid >> 1][tid & 1] = (int)0xff800000;   // -inf
@@ -152,7 +197,6 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
-  const uint32_t uU = smem_u32(sm.U), uG = smem_u32(sm.Gb);
   const int nsplit = P.nsplit;
 
   if (warp < WN_EPI_WARPS) {
@@ -163,16 +207,24 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + tile * WN_TMEM_TILE;
     uint32_t n_gate = 0, n_rs = 0, n_w = 0;          // completed phases of bar_gate / bar_rs / weight ring
     unsigned char* const Urow = sm.U + (16 + o) * 16;
-    unsigned char* const Grow = sm.Gb + o * 16;
+    {
+      uint32_t one[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) one[i] = 0u;
+      one[0] = 0x3c003c00u;   // (1.0h, 1.0h)
+      tmem_st16(tbase + WN_C_ONE, one);
+      tmem_st_wait();
+    }
+    const u64 ZERO2 = pk(0.f, 0.f), ONE2 = pk(1.f, 1.f);
 
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
       const int64_t b = grp * WN_G + w;
       const bool valid = (w < WN_G) && (t < L) && (b < n_win);
-      float x[16], skip[32];
+      u64 x[8], skip[16];     // channel pairs
       // ---- input layer: x = ReLU(in_w * mel + in_b); u0 = BN_0(x) ----
       {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) x[c] = sm.head.in_b[c];
+        for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const u64*>(sm.head.in_b + 2 * c);
         if (valid) {
           const float4* row = reinterpret_cast<const float4*>(win_row(P.wm, b, t));
 #pragma unroll
@@ -181,35 +233,37 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             const float mm[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4* wr = reinterpret_cast<const float4*>(sm.head.in_w + (k4 * 4 + j) * 16);
+              const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(sm.head.in_w + (k4 * 4 + j) * 16);
+              const u64 m2 = pk(mm[j], mm[j]);
 #pragma unroll
               for (int c4 = 0; c4 < 4; ++c4) {
-                const float4 wv = wr[c4];
-                x[c4 * 4] = fmaf(wv.x, mm[j], x[c4 * 4]);
-                x[c4 * 4 + 1] = fmaf(wv.y, mm[j], x[c4 * 4 + 1]);
-                x[c4 * 4 + 2] = fmaf(wv.z, mm[j], x[c4 * 4 + 2]);
-                x[c4 * 4 + 3] = fmaf(wv.w, mm[j], x[c4 * 4 + 3]);
+                const ulonglong2 wv = wr[c4];
+                x[c4 * 2] = ffma2(wv.x, m2, x[c4 * 2]);
+                x[c4 * 2 + 1] = ffma2(wv.y, m2, x[c4 * 2 + 1]);
               }
             }
           }
         }
 #pragma unroll
-        for (int c = 0; c < 16; ++c) x[c] = fmaxf(x[c], 0.f);
+        for (int c = 0; c < 8; ++c) x[c] = relu2(x[c]);
 #pragma unroll
-        for (int n = 0; n < 32; ++n) skip[n] = 0.f;
-        if (valid) {
+        for (int n = 0; n < 16; ++n) skip[n] = ZERO2;
+        uint32_t ur[16];
 #pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            float u[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              u[i] = __fadd_rn(__fmul_rn(x[h8 * 8 + i], sm.head.bn0_mul[h8 * 8 + i]), sm.head.bn0_add[h8 * 8 + i]);
-            uint4 hi, lo;
-            split8(u, hi, lo);
-            *reinterpret_cast<uint4*>(Urow + h8 * WN_PU) = hi;
-            *reinterpret_cast<uint4*>(Urow + 2 * WN_PU + h8 * WN_PU) = lo;
-          }
+        for (int c = 0; c < 8; ++c) {
+          const u64 u = ffma2(x[c], *reinterpret_cast<const u64*>(sm.head.bn0_mul + 2 * c),
+                              *reinterpret_cast<const u64*>(sm.head.bn0_add + 2 * c));
+          split2(u, ur[c], ur[8 + c]);
         }
+        if (valid) {
+          *reinterpret_cast<uint4*>(Urow) = make_uint4(ur[0], ur[1], ur[2], ur[3]);
+          *reinterpret_cast<uint4*>(Urow + WN_PU) = make_uint4(ur[4], ur[5], ur[6], ur[7]);
+          *reinterpret_cast<uint4*>(Urow + 2 * WN_PU) = make_uint4(ur[8], ur[9], ur[10], ur[11]);
+          *reinterpret_cast<uint4*>(Urow + 3 * WN_PU) = make_uint4(ur[12], ur[13], ur[14], ur[15]);
+        }
+        tmem_st16(tbase + WN_C_U, ur);
+        tmem_st_wait();
+        fence_before_sync();
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.bar_u[tile]);
@@ -218,31 +272,39 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       for (int k = 0; k < 24; ++k, ++n_w) {
         const int ws = n_w % WN_WST;
         mbar_wait(&sm.wfull[ws], (n_w / WN_WST) & 1);
-        const float* wf = reinterpret_cast<const float*>(sm.W[ws] + WN_GATE_B + WN_RS_B);   // gate_b[32] rs_b[48] bn_mul[16] bn_add[16]
+        const float* wf = reinterpret_cast<const float*>(sm.W[ws] + WN_OFF_F32);
         // ---- epilogue 1: gated activation ----
         mbar_wait(&sm.bar_gate[tile], n_gate & 1);
         ++n_gate;
         fence_after_sync();
         if (q == 0 && lane == 0) WN_DBG(tile, k, 0);
+        {
+          uint32_t gr[16];
 #pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          float at[8], as[8];
-          tmem_ld8(tbase + h8 * 8, at);
-          tmem_ld8(tbase + 16 + h8 * 8, as);
-          tmem_ld_wait();
-          float g[8], bt[8], bs[8];
-          ld8f(wf + h8 * 8, bt);
-          ld8f(wf + 16 + h8 * 8, bs);
+          for (int h8 = 0; h8 < 2; ++h8) {
+            float at[8], as[8];
+            tmem_ld8(tbase + h8 * 8, at);
+            tmem_ld8(tbase + 16 + h8 * 8, as);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            g[i] = gate_fn(fmaf(at[i], -2.8853900817779268f, bt[i]), fmaf(as[i], -1.4426950408889634f, bs[i]));
-          uint4 hi, lo;
-          split8(g, hi, lo);
-          *reinterpret_cast<uint4*>(Grow + h8 * WN_PG) = hi;
-          *reinterpret_cast<uint4*>(Grow + 2 * WN_PG + h8 * WN_PG) = lo;
+            for (int p = 0; p < 4; ++p) {
+              // accumulators arrive as a2 = -2*log2(e)*(a + b_t), b2 = -log2(e)*(b + b_s) (scaled weights, bias GEMM)
+              const float a0 = at[2 * p], a1 = at[2 * p + 1], b0 = as[2 * p], b1 = as[2 * p + 1];
+              // only e^(-2a) can make the quotient inf/inf, so only it is clamped (tanh is +-1 to 1e-13 there)
+              const float ea0 = ex2_approx(fminf(a0, 43.f)), ea1 = ex2_approx(fminf(a1, 43.f));
+              const float eb0 = ex2_approx(b0), eb1 = ex2_approx(b1);   // e^(-b); inf -> rcp(inf) = 0 -> g = 0
+              const u64 tt = fadd2(pk(eb0, eb1), ONE2);
+              float d0, d1;
+              upk(ffma2(pk(ea0, ea1), tt, tt), d0, d1);                 // (1 + e^-2a)(1 + e^-b)
+              const float r0 = rcp_approx(d0), r1 = rcp_approx(d1);
+              const u64 g = pk(fmaf(-ea0, r0, r0), fmaf(-ea1, r1, r1)); // tanh(a) * sigmoid(b)
+              split2(g, gr[h8 * 4 + p], gr[8 + h8 * 4 + p]);
+            }
+          }
+          tmem_st16(tbase + WN_C_G, gr);
+          tmem_st_wait();
         }
         fence_before_sync();
-        fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.bar_g[tile]);
         if (q == 0 && lane == 0) WN_DBG(tile, k, 1);
@@ -253,57 +315,53 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         fence_after_sync();
         if (q == 0 && lane == 0) WN_DBG(tile, k, 2);
         const bool last = (k == 23);
+        if (!last) {
+          uint32_t ur[16];
 #pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          float r[8];
-          tmem_ld8(tbase + 32 + h8 * 8, r);
-          tmem_ld_wait();
-          if (!last) {
-            float u[8], br[8], bm[8], ba[8];
-            ld8f(wf + 32 + h8 * 8, br);
-            ld8f(wf + 80 + h8 * 8, bm);
-            ld8f(wf + 96 + h8 * 8, ba);
+          for (int h8 = 0; h8 < 2; ++h8) {
+            float r[8];
+            tmem_ld8(tbase + h8 * 8, r);
+            tmem_ld_wait();
+            const ulonglong2* bm = reinterpret_cast<const ulonglong2*>(wf + 80 + h8 * 8);
+            const ulonglong2* ba = reinterpret_cast<const ulonglong2*>(wf + 96 + h8 * 8);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int c = h8 * 8 + i;
-              x[c] = fmaxf(r[i] + br[i], 0.f) + x[c];
-              u[i] = fmaf(x[c], bm[i], ba[i]);
-            }
-            if (valid) {
-              uint4 hi, lo;
-              split8(u, hi, lo);
-              *reinterpret_cast<uint4*>(Urow + h8 * WN_PU) = hi;
-              *reinterpret_cast<uint4*>(Urow + 2 * WN_PU + h8 * WN_PU) = lo;
+            for (int p = 0; p < 4; ++p) {
+              const ulonglong2 bmv = bm[p >> 1], bav = ba[p >> 1];
+              const int c = h8 * 4 + p;
+              x[c] = fadd2(relu2(pk(r[2 * p], r[2 * p + 1])), x[c]);
+              const u64 u = ffma2(x[c], (p & 1) ? bmv.y : bmv.x, (p & 1) ? bav.y : bav.x);
+              split2(u, ur[c], ur[8 + c]);
             }
           }
+          if (valid) {
+            *reinterpret_cast<uint4*>(Urow) = make_uint4(ur[0], ur[1], ur[2], ur[3]);
+            *reinterpret_cast<uint4*>(Urow + WN_PU) = make_uint4(ur[4], ur[5], ur[6], ur[7]);
+            *reinterpret_cast<uint4*>(Urow + 2 * WN_PU) = make_uint4(ur[8], ur[9], ur[10], ur[11]);
+            *reinterpret_cast<uint4*>(Urow + 3 * WN_PU) = make_uint4(ur[12], ur[13], ur[14], ur[15]);
+          }
+          tmem_st16(tbase + WN_C_U, ur);
         }
 #pragma unroll
         for (int h8 = 0; h8 < 4; ++h8) {
-          float s[8], bk[8];
-          tmem_ld8(tbase + 48 + h8 * 8, s);
-          ld8f(wf + 48 + h8 * 8, bk);
+          float s[8];
+          tmem_ld8(tbase + 16 + h8 * 8, s);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) skip[h8 * 8 + i] += fmaxf(s[i] + bk[i], 0.f);
-        }
-        if (last) {
-          // detect input: ReLU(skip) hi/lo; channels 0-15 -> G panels, 16-31 -> U panels
-#pragma unroll
-          for (int h8 = 0; h8 < 4; ++h8) {
-            float e[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] = fmaxf(skip[h8 * 8 + i], 0.f);
-            uint4 hi, lo;
-            split8(e, hi, lo);
-            if (h8 < 2) {
-              *reinterpret_cast<uint4*>(Grow + h8 * WN_PG) = hi;
-              *reinterpret_cast<uint4*>(Grow + 2 * WN_PG + h8 * WN_PG) = lo;
-            } else if (valid) {
-              *reinterpret_cast<uint4*>(Urow + (h8 - 2) * WN_PU) = hi;
-              *reinterpret_cast<uint4*>(Urow + 2 * WN_PU + (h8 - 2) * WN_PU) = lo;
-            }
+          for (int p = 0; p < 4; ++p) {
+            skip[h8 * 4 + p] = fadd2(skip[h8 * 4 + p], relu2(pk(s[2 * p], s[2 * p + 1])));
           }
         }
+        if (last) {
+          // detect input: ReLU(skip) hi/lo; channels 0-15 -> the u columns, 16-31 -> the g columns
+          uint32_t er[16];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) split2(relu2(skip[c]), er[c], er[8 + c]);
+          tmem_st16(tbase + WN_C_U, er);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) split2(relu2(skip[8 + c]), er[c], er[8 + c]);
+          tmem_st16(tbase + WN_C_G, er);
+        }
+        tmem_st_wait();
         fence_before_sync();
         fence_async_smem();
         __syncwarp();
@@ -314,7 +372,12 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       if (P.enc_out && valid) {
         float4* dst = reinterpret_cast<float4*>(P.enc_out + (b * L + t) * 32);
 #pragma unroll
-        for (int n = 0; n < 32; n += 4) dst[n / 4] = make_float4(skip[n], skip[n + 1], skip[n + 2], skip[n + 3]);
+        for (int n = 0; n < 8; ++n) {
+          float s0, s1, s2, s3;
+          upk(skip[2 * n], s0, s1);
+          upk(skip[2 * n + 1], s2, s3);
+          dst[n] = make_float4(s0, s1, s2, s3);
+        }
       }
       // ---- detect head epilogue: ReLU(D + b1) -> 32->2 -> max over time ----
       mbar_wait(&sm.bar_gate[tile], n_gate & 1);
@@ -355,109 +418,126 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     }
   } else {
     // =========================== MMA issuer + weight loader ===========================
-    // Per block: all five gate GEMMs first (each as soon as its tile's U is ready), then the
-    // five res/skip GEMMs (each as soon as its tile's g is ready).  rs(k,i) is therefore always
-    // issued after gate(k,i+1), which reads the last rows of tile i's U through the row-shifted
-    // taps and must finish before epilogue 2 of (k,i) overwrites them (tcgen05 ops of one thread
-    // complete in order).  Tiles run staggered: while tile 4 is still in epilogue 1 of block k,
-    // tile 0 is already in epilogue 2, which keeps the SFU and FMA pipes both busy.
-    // The weight ring is refilled right after the gate GEMMs of block k are issued: by then
-    // every tile has finished block k-1, so the other stage is free.
+    // Static software-pipelined order with blocking (sleeping) mbarrier waits; per block k:
+    //     G0 R3' G1 R4' G2 R0 G3 R1 G4 R2          (G = gate GEMM, R = res/skip GEMM, ' = block k-1)
+    // i.e. tile i+3's res/skip GEMM is issued half a period after its gate GEMM, which is where the
+    // evenly staggered steady state puts it.  The order also satisfies the hazard rule (header): R_i
+    // follows G_{i+1} of the same block.  All descriptors are a loop-invariant base plus a small
+    // uniform offset, so an issue slot is ~40 uniform-datapath instructions.
     const uint32_t idesc_gate = make_idesc_f16(128, 32), idesc_rs = make_idesc_f16(128, 48);
-    const uint32_t hb = smem_u32(sm.head.det1_B);
-    uint32_t n_u = 0, n_g = 0, n_w = 0, n_load = 0;
+    const uint64_t dU = make_desc(smem_u32(sm.U), WN_PU, 128);                   // U row 0, hi plane
+    const uint64_t dWg = make_desc(smem_u32(sm.W[0]), 512, 128);                 // gate B: stage 0, tap 0, hi plane
+    const uint64_t dWr = make_desc(smem_u32(sm.W[0]) + WN_GATE_B, 768, 128);     // res/skip B: stage 0, hi plane
+    const uint64_t dBg = make_desc(smem_u32(sm.W[0]) + WN_OFF_GBIAS, 512, 128);  // gate bias B: stage 0
+    const uint64_t dBr = make_desc(smem_u32(sm.W[0]) + WN_OFF_RBIAS, 768, 128);  // res/skip bias B: stage 0
+    const uint64_t dH = make_desc(smem_u32(sm.head.det1_B), 512, 128);           // detect B: k-step 0, hi plane
     uint32_t my_groups = 0;
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) ++my_groups;
     const uint32_t total_loads = my_groups * 24;
-    // prologue: fill WN_WST-1 stages
-    for (; n_load < (uint32_t)(WN_WST - 1) && n_load < total_loads; ++n_load)
+    for (uint32_t n = 0; n < (uint32_t)WN_WST && n < total_loads; ++n)
       if (lane == 0) {
-        mbar_arrive_expect_tx(&sm.wfull[n_load % WN_WST], WN_WBLK);
-        bulk_g2s(sm.W[n_load % WN_WST], P.wblob + (size_t)(n_load % 24) * WN_WBLK, WN_WBLK, &sm.wfull[n_load % WN_WST]);
+        mbar_arrive_expect_tx(&sm.wfull[n], WN_WBLK);
+        bulk_g2s(sm.W[n], P.wblob + (size_t)n * WN_WBLK, WN_WBLK, &sm.wfull[n]);
       }
-    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-      for (int k = 0; k < 24; ++k, ++n_w) {
-        const int ws = n_w % WN_WST;
-        mbar_wait(&sm.wfull[ws], (n_w / WN_WST) & 1);
-        const int d = P.dil[k];
-        const uint32_t wb = smem_u32(sm.W[ws]);
+    uint32_t nb = 0;          // global block index (24 per group)
+    uint32_t ubase = 0;       // bar_u phases before this group (25 per group), bar_g phases = nb
+    auto issue_rs = [&](const int j, const uint32_t blk, const int kk, const int64_t grp) {
+      if (j == 3) WN_DBG(7, kk, 0);
+      mbar_wait(&sm.bar_g[j], blk & 1);
+      if (j == 3) WN_DBG(7, kk, 1);
+      fence_after_sync();
+      if (elect_one()) {
+        const uint32_t tacc = tmem + j * WN_TMEM_TILE;
+        const uint64_t bh = dWr + (uint64_t)((blk % WN_WST) * (WN_WBLK >> 4)), bl = bh + (uint64_t)(1536 >> 4);
+        mma_f16_ts(tacc, tacc + WN_C_G, bh, idesc_rs, false);
+        if (nsplit == 3) {
+          mma_f16_ts(tacc, tacc + WN_C_G + 8, bh, idesc_rs, true);
+          mma_f16_ts(tacc, tacc + WN_C_G, bl, idesc_rs, true);
+        }
+        mma_f16_ts(tacc, tacc + WN_C_ONE, dBr + (uint64_t)((blk % WN_WST) * (WN_WBLK >> 4)), idesc_rs, true);
+        mma_commit(&sm.bar_rs[j]);
+        if (j == 0) WN_DBG(5, kk, 2);
+        if (j == WN_NT - 1) WN_DBG(5, kk, 3);
+      }
+      __syncwarp();
+      if (j == 3) WN_DBG(7, kk, 2);
+    };
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ubase += 25) {
+      for (int k = 0; k < 24; ++k, ++nb) {
+        mbar_wait(&sm.wfull[nb % WN_WST], (nb / WN_WST) & 1);
+        const uint32_t d = (uint32_t)P.dil[k];
+        const uint64_t dWk = dWg + (uint64_t)((nb % WN_WST) * (WN_WBLK >> 4));
+#pragma unroll
         for (int i = 0; i < WN_NT; ++i) {
-          mbar_wait(&sm.bar_u[i], n_u & 1);
+          if (i == 1) WN_DBG(6, k, 0);
+          mbar_wait(&sm.bar_u[i], (ubase + k) & 1);
+          if (i == 1) WN_DBG(6, k, 1);
           fence_after_sync();
           if (elect_one()) {   // one lane issues the whole tile (uniform descriptors, no per-MMA election)
-            const uint32_t dst = tmem + i * WN_TMEM_TILE;
-            const uint64_t db = make_desc(wb, 512, 128);
+            const uint32_t tacc = tmem + i * WN_TMEM_TILE;
 #pragma unroll
-            for (int tap = 0; tap < 3; ++tap) {
-              const uint32_t arow = (uint32_t)(16 + i * 128 - (2 - tap) * d) * 16;
-              const uint64_t ah = make_desc(uU + arow, WN_PU, 128), al = ah + (uint64_t)((2 * WN_PU) >> 4);
-              const uint64_t bh = db + (uint64_t)((tap * 2 * 512) >> 4), bl = bh + (uint64_t)(3072 >> 4);
-              mma_f16_ss(dst, ah, bh, idesc_gate, tap != 0);
+            for (int tap = 0; tap < 2; ++tap) {
+              const uint64_t ah = dU + (uint64_t)(16 + i * 128 - (2 - tap) * d), al = ah + (uint64_t)((2 * WN_PU) >> 4);
+              const uint64_t bh = dWk + (uint64_t)((tap * 2 * 512) >> 4), bl = bh + (uint64_t)(3072 >> 4);
+              mma_f16_ss(tacc, ah, bh, idesc_gate, tap != 0);
               if (nsplit == 3) {
-                mma_f16_ss(dst, al, bh, idesc_gate, true);
-                mma_f16_ss(dst, ah, bl, idesc_gate, true);
+                mma_f16_ss(tacc, al, bh, idesc_gate, true);
+                mma_f16_ss(tacc, ah, bl, idesc_gate, true);
               }
+            }
+            {
+              const uint64_t bh = dWk + (uint64_t)((2 * 2 * 512) >> 4), bl = bh + (uint64_t)(3072 >> 4);
+              mma_f16_ts(tacc, tacc + WN_C_U, bh, idesc_gate, true);
+              if (nsplit == 3) {
+                mma_f16_ts(tacc, tacc + WN_C_U + 8, bh, idesc_gate, true);
+                mma_f16_ts(tacc, tacc + WN_C_U, bl, idesc_gate, true);
+              }
+              mma_f16_ts(tacc, tacc + WN_C_ONE, dBg + (uint64_t)((nb % WN_WST) * (WN_WBLK >> 4)), idesc_gate, true);
             }
             mma_commit(&sm.bar_gate[i]);
             if (i == 0) WN_DBG(5, k, 0);
             if (i == WN_NT - 1) WN_DBG(5, k, 1);
           }
           __syncwarp();
-        }
-        ++n_u;
-        // all tiles have finished block k-1, so the stage that held its weights is free:
-        // refill it with the block WN_WST-1 ahead (bulk copies take ~2.4 us, i.e. > one block)
-        if (n_load < total_loads) {
-          if (lane == 0) {
-            mbar_arrive_expect_tx(&sm.wfull[n_load % WN_WST], WN_WBLK);
-            bulk_g2s(sm.W[n_load % WN_WST], P.wblob + (size_t)(n_load % 24) * WN_WBLK, WN_WBLK, &sm.wfull[n_load % WN_WST]);
-          }
-          ++n_load;
-        }
-        for (int i = 0; i < WN_NT; ++i) {
-          mbar_wait(&sm.bar_g[i], n_g & 1);
-          fence_after_sync();
-          if (elect_one()) {
-            const uint32_t dst = tmem + i * WN_TMEM_TILE + 32;
-            const uint32_t arow = (uint32_t)(i * 128) * 16;
-            const uint64_t ah = make_desc(uG + arow, WN_PG, 128), al = ah + (uint64_t)((2 * WN_PG) >> 4);
-            const uint64_t bh = make_desc(wb + WN_GATE_B, 768, 128), bl = bh + (uint64_t)(1536 >> 4);
-            mma_f16_ss(dst, ah, bh, idesc_rs, false);
-            if (nsplit == 3) {
-              mma_f16_ss(dst, al, bh, idesc_rs, true);
-              mma_f16_ss(dst, ah, bl, idesc_rs, true);
+          if (i == 1) WN_DBG(6, k, 2);
+          if (i == WN_NT - 1 && nb >= 1 && nb - 1 + WN_WST < total_loads) {
+            // every tile has finished block nb-1 (its epilogue 2 was awaited above): refill that stage
+            const uint32_t nl = nb - 1 + WN_WST;
+            if (lane == 0) {
+              mbar_arrive_expect_tx(&sm.wfull[nl % WN_WST], WN_WBLK);
+              bulk_g2s(sm.W[nl % WN_WST], P.wblob + (size_t)(nl % 24) * WN_WBLK, WN_WBLK, &sm.wfull[nl % WN_WST]);
             }
-            mma_commit(&sm.bar_rs[i]);
-            if (i == 0) WN_DBG(5, k, 2);
-            if (i == WN_NT - 1) WN_DBG(5, k, 3);
           }
-          __syncwarp();
+          if (i < 2) {
+            if (k > 0) issue_rs(i + 3, nb - 1, k - 1, grp);
+          } else {
+            issue_rs(i - 2, nb, k, grp);
+          }
         }
-        ++n_g;
       }
-      // detect head: D[128,32] = ReLU(skip)[128,32] * W1^T ; k-step 0 from G panels, k-step 1 from U panels
+      issue_rs(3, nb - 1, 23, grp);
+      issue_rs(4, nb - 1, 23, grp);
+      // detect head: D[128,32] = ReLU(skip)[128,32] * W1^T ; k-step 0 from the u columns, k-step 1 from the g columns
+#pragma unroll
       for (int i = 0; i < WN_NT; ++i) {
-        mbar_wait(&sm.bar_u[i], n_u & 1);
+        mbar_wait(&sm.bar_u[i], (ubase + 24) & 1);
         fence_after_sync();
         if (elect_one()) {
-          const uint32_t dst = tmem + i * WN_TMEM_TILE;
+          const uint32_t tacc = tmem + i * WN_TMEM_TILE;
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
-            const uint32_t abase = kk == 0 ? uG + (uint32_t)(i * 128) * 16 : uU + (uint32_t)(16 + i * 128) * 16;
-            const uint32_t pl = kk == 0 ? WN_PG : WN_PU;
-            const uint64_t ah = make_desc(abase, pl, 128), al = make_desc(abase + 2 * pl, pl, 128);
-            const uint64_t bh = make_desc(hb + kk * 2 * 512, 512, 128), bl = make_desc(hb + 2048 + kk * 2 * 512, 512, 128);
-            mma_f16_ss(dst, ah, bh, idesc_gate, kk != 0);
+            const uint32_t ta = tacc + (kk == 0 ? WN_C_U : WN_C_G);
+            const uint64_t bh = dH + (uint64_t)((kk * 2 * 512) >> 4), bl = bh + (uint64_t)(2048 >> 4);
+            mma_f16_ts(tacc, ta, bh, idesc_gate, kk != 0);
             if (nsplit == 3) {
-              mma_f16_ss(dst, al, bh, idesc_gate, true);
-              mma_f16_ss(dst, ah, bl, idesc_gate, true);
+              mma_f16_ts(tacc, ta + 8, bh, idesc_gate, true);
+              mma_f16_ts(tacc, ta, bl, idesc_gate, true);
             }
           }
           mma_commit(&sm.bar_gate[i]);
         }
         __syncwarp();
       }
-      ++n_u;
     }
   }
   fence_before_sync();
@@ -466,6 +546,9 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
 }
 
 // ---- host side: pack the weights ------------------------------------------------------------
+// the gate pre-activations are produced pre-scaled for ex2: tanh half by -2*log2(e), sigmoid half by -log2(e)
+static double gate_scale(int n) { return n < 16 ? -2.8853900817779268 : -1.4426950408889634; }
+
 static void put_split(std::vector<unsigned char>& buf, size_t hi_off, size_t lo_off, float x, bool split) {
   __half h = __float2half_rn(x);
   __half l = split ? __float2half_rn(x - __half2float(h)) : __float2half_rn(0.f);
@@ -485,7 +568,7 @@ std::vector<unsigned char> wavenet_pack_blocks(const float* gate_w, const float*
       for (int n = 0; n < 32; ++n) {
         const int c = k / 8, e = k % 8;
         const size_t off = base + ((size_t)c * 32 + n) * 16 + e * 2;
-        put_split(out, off, off + 3072, gate_w[((size_t)b * 48 + k) * 32 + n], true);
+        put_split(out, off, off + 3072, (float)((double)gate_w[((size_t)b * 48 + k) * 32 + n] * gate_scale(n)), true);
       }
     for (int k = 0; k < 16; ++k)
       for (int n = 0; n < 48; ++n) {
@@ -494,13 +577,19 @@ std::vector<unsigned char> wavenet_pack_blocks(const float* gate_w, const float*
         put_split(out, off, off + 1536, rs_w[((size_t)b * 16 + k) * 48 + n], true);
       }
     float f[113] = {0};
-    for (int n = 0; n < 32; ++n)   // pre-scaled for gate_fn: tanh half by -2*log2(e), sigmoid half by -log2(e)
-      f[n] = (float)((double)gate_b[b * 32 + n] * (n < 16 ? -2.8853900817779268 : -1.4426950408889634));
-    for (int n = 0; n < 48; ++n) f[32 + n] = rs_b[b * 48 + n];
     if (b < 23)
       for (int c = 0; c < 16; ++c) { f[80 + c] = bn_mul[(b + 1) * 16 + c]; f[96 + c] = bn_add[(b + 1) * 16 + c]; }
     f[112] = (float)dilation[b];
-    memcpy(&out[base + WN_GATE_B + WN_RS_B], f, sizeof(f));
+    memcpy(&out[base + WN_OFF_F32], f, sizeof(f));
+    // bias operands of the 'ones' GEMM: row n = (hi, lo, 0, ...); the second k-chunk stays zero
+    for (int n = 0; n < 32; ++n) {
+      const size_t off = base + WN_OFF_GBIAS + (size_t)n * 16;
+      put_split(out, off, off + 2, (float)((double)gate_b[b * 32 + n] * gate_scale(n)), true);
+    }
+    for (int n = 0; n < 48; ++n) {
+      const size_t off = base + WN_OFF_RBIAS + (size_t)n * 16;
+      put_split(out, off, off + 2, rs_b[b * 48 + n], true);
+    }
   }
   return out;
 }
