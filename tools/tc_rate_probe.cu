@@ -16,7 +16,7 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uin
       : "memory");
 }
 
-template <int N, int M, bool TS>
+template <int N, int M, bool TS, int NACC = 2>
 __global__ void rate_kernel(int reps, long long* out) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar;
@@ -36,8 +36,8 @@ __global__ void rate_kernel(int reps, long long* out) {
       for (int r = 0; r < reps; ++r) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          if (TS) mma_f16_ts(tmem + (j & 1) * 256, tmem + 480, db, idesc, true);
-          else mma_f16_ss(tmem + (j & 1) * 256, da, db, idesc, true);
+          if (TS) mma_f16_ts(tmem + (j % NACC) * 64, tmem + 480, db, idesc, true);
+          else mma_f16_ss(tmem + (j % NACC) * 64, da, db, idesc, true);
         }
       }
       mma_commit(&bar);
@@ -52,15 +52,15 @@ __global__ void rate_kernel(int reps, long long* out) {
   if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
-template <int N, int M, bool TS>
+template <int N, int M, bool TS, int NACC = 2>
 void run(long long* d) {
-  cudaFuncSetAttribute(rate_kernel<N, M, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 61440);
+  cudaFuncSetAttribute(rate_kernel<N, M, TS, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 61440);
   long long h[2][2];
   for (int i = 0; i < 2; ++i) {
-    rate_kernel<N, M, TS><<<1, 128, 61440>>>(i == 0 ? 2 : 10, d);
+    rate_kernel<N, M, TS, NACC><<<1, 128, 61440>>>(i == 0 ? 2 : 10, d);
     if (cudaMemcpy(h[i], d, 16, cudaMemcpyDeviceToHost) != cudaSuccess) { printf("error\n"); exit(1); }
   }
-  printf("M=%3d N=%3d %s : %.1f clk/MMA (pipe), issue %.1f clk/MMA\n", M, N, TS ? "A=tmem" : "A=smem",
+  printf("M=%3d N=%3d %s n_acc=%d : %.1f clk/MMA (pipe), issue %.1f clk/MMA\n", M, N, TS ? "A=tmem" : "A=smem", NACC,
          (double)(h[1][1] - h[0][1]) / (8 * 16), (double)(h[1][0] - h[0][0]) / (8 * 16));
 }
 
@@ -72,5 +72,10 @@ int main() {
   run<128, 128, true>(d); run<256, 128, true>(d);
   run<32, 64, false>(d); run<64, 64, false>(d); run<128, 64, false>(d); run<256, 64, false>(d);
   run<32, 64, true>(d); run<256, 64, true>(d);
+  // dependent chains: every MMA accumulates into the same TMEM columns (n_acc = 1) vs. 2 / 4 independent accumulators
+  run<32, 128, true, 1>(d); run<32, 128, true, 2>(d); run<32, 128, true, 4>(d);
+  run<48, 128, true, 1>(d); run<48, 128, true, 4>(d);
+  run<32, 128, false, 1>(d); run<32, 128, false, 2>(d); run<32, 128, false, 4>(d);
+  run<64, 128, false, 1>(d); run<64, 128, true, 1>(d);
   return 0;
 }

@@ -22,11 +22,13 @@
 // (DESIGN.md §precision).  Epilogue arithmetic uses the packed fp32x2 instructions (FFMA2/FADD2).
 // Per-block weights (9.5 KB) stream through a 4-stage cp.async.bulk ring.
 //
-// The MMA warp issues in a static software-pipelined order (see the issuer) so that tiles run staggered:
-// the tensor pipe, the SFU and the FMA/ALU pipes are busy with different tiles at the same time.
+// GEMM issue: one extra warp issues the gate GEMMs tile after tile (in order, so they run back to back and
+// stagger the tiles: the tensor pipe, the SFU and the FMA/ALU pipes then work on different tiles at the
+// same time); the small res/skip GEMM is issued by the LAST of the tile's four warps to finish epilogue 1
+// (shared-memory arrival counter), i.e. without a round trip through the issuing warp.  Ordering rules:
 //   gate(k,i) needs epilogue 2 of (k-1,i) and (k-1,i-1)      (its taps reach 16 rows into tile i-1)
-//   rs(k,i)   needs epilogue 1 of (k,i) and gate(k,i+1) ISSUED: epilogue 2 of (k,i) overwrites rows
-//             gate(k,i+1) reads, and tcgen05 ops of one thread complete in order.
+//   rs(k,i)   needs epilogue 1 of (k,i) and gate(k,i+1) COMPLETE: epilogue 2 of (k,i) overwrites rows that
+//             GEMM reads, and GEMMs issued by different threads have no implicit order.
 #include <string.h>
 
 #include "common.cuh"
@@ -44,7 +46,7 @@ constexpr int WN_UROWS = WN_ROWS + 16;        // U buffer has 16 leading zero ro
 constexpr int WN_PU = WN_UROWS * 16;          // bytes per U chunk panel
 constexpr int WN_EPI_WARPS = WN_NT * 4;       // 20
 constexpr int WN_EPI_THREADS = WN_EPI_WARPS * 32;
-constexpr int WN_THREADS = (WN_EPI_WARPS + 1) * 32;   // + MMA/loader warp = 672 (leaves 96 registers per thread)
+constexpr int WN_THREADS = (WN_EPI_WARPS + 1) * 32;   // + the gate-GEMM / loader warp = 672
 constexpr int WN_GATE_B = 6144, WN_RS_B = 3072;   // gate / res+skip B operands (hi and lo planes)
 constexpr int WN_F32_B = 512;                     // fp32 constants: [80..95] next block's BN scale, [96..111] BN shift
 constexpr int WN_GBIAS_B = 1024, WN_RBIAS_B = 1536;   // bias B operands for the 'ones' GEMM (k0 = hi, k1 = lo)
@@ -72,7 +74,9 @@ struct WnSmem {
   unsigned char U[2 * 2 * WN_PU];          // [plane][chunk][row]
   unsigned char W[WN_WST][WN_WBLK];
   WnHead head;
-  uint64_t bar_u[WN_NT], bar_gate[WN_NT], bar_g[WN_NT], bar_rs[WN_NT];
+  uint64_t bar_gate[WN_NT], bar_rs[WN_NT], bar_det[WN_NT];   // GEMM completion (tcgen05.commit) -> the tile's four warps
+  uint64_t bar_u[WN_NT];                     // the tile's four warps finished epilogue 2 -> gate warp
+  uint32_t cnt_g[WN_NT];                     // warps that finished epilogue 1 (monotonic): the last one issues the res/skip GEMM
   uint64_t wfull[WN_WST];
   uint32_t tmem_base;
   int zmax[WN_G][2];
@@ -170,6 +174,63 @@ __device__ __forceinline__ void atomic_max_float(int* addr, float v) {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(WN_EPI_THREADS) : "memory"); }
 
+// ---- cross-warp progress counters (shared memory) ------------------------------------------
+// Each warp adds 1 when it has finished a step for its tile; the warp that brings the count to a
+// multiple of 4 is the last of the tile and issues the tile's next GEMM itself.
+__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
+// all lanes call; true (in every lane) for the last of the tile's four warps.  Release/acquire at CTA scope.
+__device__ __forceinline__ bool arrive_is_last(uint32_t* cnt, int lane) {
+  uint32_t old = 0;
+  __syncwarp();
+  if (lane == 0) old = atom_add_acq_rel_shared(cnt, 1u);
+  old = __shfl_sync(0xffffffffu, old, 0);
+  return (old & 3u) == 3u;
+}
+// wait until *cnt >= target (lane 0 polls)
+__device__ __forceinline__ void wait_count(const uint32_t* cnt, uint32_t target, int lane) {
+  if (lane == 0) {
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_shared(cnt) - target) < 0) {
+      if (++spins > (1u << 26)) __trap();
+    }
+  }
+  __syncwarp();
+}
+
+// ---- hang diagnosis (compile with -DWWB_HANG_DEBUG and pass a debug buffer): instead of trapping, the first
+// thread whose wait times out dumps its position and the shared progress counters behind the timeline
+// area of the debug buffer, and every timed-out thread exits, so the kernel ends and the host can read it.
+#ifdef WWB_HANG_DEBUG
+#define WN_SPIN_LIMIT (1u << 17)
+__device__ __noinline__ void wn_hang(long long* dbg, const uint32_t* cnt_u, const uint32_t* cnt_g, int id, int tile, int q,
+                                     uint32_t n_gate, uint32_t n_rs, uint32_t n_u, uint32_t n_w) {
+  if (dbg) {
+    long long* base = dbg + 8 * 24 * 4;
+    if (atomicCAS(reinterpret_cast<unsigned long long*>(base), 0ull, 1ull) == 0ull) {
+      base[1] = id; base[2] = blockIdx.x; base[3] = tile; base[4] = q; base[5] = n_gate; base[6] = n_rs;
+      base[7] = n_u; base[8] = n_w;
+      for (int i = 0; i < 5; ++i) { base[9 + i] = cnt_u[i]; base[14 + i] = cnt_g[i]; }
+    }
+  }
+  asm volatile("exit;");
+}
+#define WN_HANG(id) wn_hang(P.dbg, sm.cnt_g, sm.cnt_g, id, tile, q, n_gate, n_rs, n_u, n_w)
+#define WN_MBAR_WAIT(bar, par, id) do { if (!mbar_try_wait(bar, par)) { uint32_t sp_ = 0; while (!mbar_try_wait(bar, par)) if (++sp_ > WN_SPIN_LIMIT) WN_HANG(id); } } while (0)
+#define WN_WAIT_COUNT(cnt, target, id) do { if (lane == 0) { uint32_t sp_ = 0; while ((int32_t)(ld_acquire_shared(cnt) - (target)) < 0) if (++sp_ > (WN_SPIN_LIMIT << 4)) WN_HANG(id); } __syncwarp(); } while (0)
+#else
+#define WN_MBAR_WAIT(bar, par, id) mbar_wait(bar, par)
+#define WN_WAIT_COUNT(cnt, target, id) wait_count(cnt, target, lane)
+#endif
+
 __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WnSmem& sm = *reinterpret_cast<WnSmem*>(smem_raw);
@@ -184,9 +245,10 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
   for (int i = tid; i < (int)(sizeof(WnHead) / 16); i += WN_THREADS)
     reinterpret_cast<uint4*>(&sm.head)[i] = reinterpret_cast<const uint4*>(P.head)[i];
   if (tid < WN_G * 2) sm.zmax[tid >> 1][tid & 1] = (int)0xff800000;   // -inf
+  if (tid < WN_NT) sm.cnt_g[tid] = 0;
   if (tid == 0) {
     for (int i = 0; i < WN_NT; ++i) {
-      mbar_init(&sm.bar_u[i], 4); mbar_init(&sm.bar_gate[i], 1); mbar_init(&sm.bar_g[i], 4); mbar_init(&sm.bar_rs[i], 1);
+      mbar_init(&sm.bar_u[i], 4); mbar_init(&sm.bar_gate[i], 1); mbar_init(&sm.bar_rs[i], 1); mbar_init(&sm.bar_det[i], 1);
     }
     for (int s = 0; s < WN_WST; ++s) mbar_init(&sm.wfull[s], 1);
     mbar_fence_init();
@@ -198,15 +260,19 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
   fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
   const int nsplit = P.nsplit;
+  const uint32_t idesc_gate = make_idesc_f16(128, 32), idesc_rs = make_idesc_f16(128, 48);
 
   if (warp < WN_EPI_WARPS) {
     // =========================== epilogue threads: one row each ===========================
     const int tile = warp >> 2, q = warp & 3;
     const int o = tile * 128 + q * 32 + lane;       // row within the group
     const int w = o / WN_SLOT, t = o - w * WN_SLOT;
-    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + tile * WN_TMEM_TILE;
-    uint32_t n_gate = 0, n_rs = 0, n_w = 0;          // completed phases of bar_gate / bar_rs / weight ring
+    const uint32_t tacc = tmem + tile * WN_TMEM_TILE;                 // this tile's TMEM columns (lane 0)
+    const uint32_t tbase = tacc + ((uint32_t)(q * 32) << 16);         // ... seen from this warp's lane quadrant
+    uint32_t n_gate = 0, n_rs = 0, n_w = 0, n_u = 0;  // completed phases of bar_gate / bar_rs ; global block index ; groups done
     unsigned char* const Urow = sm.U + (16 + o) * 16;
+    const uint64_t dWr = make_desc(smem_u32(sm.W[0]) + WN_GATE_B, 768, 128);
+    const uint64_t dBr = make_desc(smem_u32(sm.W[0]) + WN_OFF_RBIAS, 768, 128);
     {
       uint32_t one[16];
 #pragma unroll
@@ -217,7 +283,32 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     }
     const u64 ZERO2 = pk(0.f, 0.f), ONE2 = pk(1.f, 1.f);
 
-    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    // res/skip GEMM of block k, issued by the LAST of the tile's four warps to finish epilogue 1 (all lanes call;
+    // one elected lane issues).  A = g from TMEM, + bias k-step.  Epilogue 2 of this tile will overwrite rows
+    // that gate(k) of tile+1 reads, so that GEMM must have COMPLETED (it is issued by another thread).
+    auto issue_rs = [&](const int k, const uint32_t nb, const int64_t grp) {
+      if (tile == 3) WN_DBG(7, k, 0);
+      if (tile < WN_NT - 1) WN_MBAR_WAIT(&sm.bar_gate[tile + 1], (n_gate - 1) & 1, 3);
+      if (tile == 3) WN_DBG(7, k, 1);
+      const uint64_t wofs = (uint64_t)((nb % WN_WST) * (WN_WBLK >> 4));
+      const uint64_t bh = dWr + wofs, bb = dBr + wofs;
+      fence_after_sync();
+      if (elect_one()) {
+        mma_f16_ts(tacc, tacc + WN_C_G, bh, idesc_rs, false);
+        if (nsplit == 3) {
+          mma_f16_ts(tacc, tacc + WN_C_G + 8, bh, idesc_rs, true);
+          mma_f16_ts(tacc, tacc + WN_C_G, bh + (uint64_t)(1536 >> 4), idesc_rs, true);
+        }
+        mma_f16_ts(tacc, tacc + WN_C_ONE, bb, idesc_rs, true);
+        mma_commit(&sm.bar_rs[tile]);
+      }
+      __syncwarp();
+      if (tile == 0) WN_DBG(5, k, 2);
+      if (tile == WN_NT - 1) WN_DBG(5, k, 3);
+      if (tile == 3) WN_DBG(7, k, 2);
+    };
+
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++n_u) {
       const int64_t b = grp * WN_G + w;
       const bool valid = (w < WN_G) && (t < L) && (b < n_win);
       u64 x[8], skip[16];     // channel pairs
@@ -271,10 +362,10 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
 
       for (int k = 0; k < 24; ++k, ++n_w) {
         const int ws = n_w % WN_WST;
-        mbar_wait(&sm.wfull[ws], (n_w / WN_WST) & 1);
         const float* wf = reinterpret_cast<const float*>(sm.W[ws] + WN_OFF_F32);
+        WN_MBAR_WAIT(&sm.wfull[ws], (n_w / WN_WST) & 1, 4);   // BN constants travel with the block's weights (off the critical path: the gate GEMM is running)
         // ---- epilogue 1: gated activation ----
-        mbar_wait(&sm.bar_gate[tile], n_gate & 1);
+        WN_MBAR_WAIT(&sm.bar_gate[tile], n_gate & 1, 5);
         ++n_gate;
         fence_after_sync();
         if (q == 0 && lane == 0) WN_DBG(tile, k, 0);
@@ -305,12 +396,11 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           tmem_st_wait();
         }
         fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.bar_g[tile]);
         if (q == 0 && lane == 0) WN_DBG(tile, k, 1);
+        if (arrive_is_last(&sm.cnt_g[tile], lane)) issue_rs(k, n_w, grp);
 
         // ---- epilogue 2: residual + skip, next block's BN ----
-        mbar_wait(&sm.bar_rs[tile], n_rs & 1);
+        WN_MBAR_WAIT(&sm.bar_rs[tile], n_rs & 1, 6);
         ++n_rs;
         fence_after_sync();
         if (q == 0 && lane == 0) WN_DBG(tile, k, 2);
@@ -347,9 +437,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           tmem_ld8(tbase + 16 + h8 * 8, s);
           tmem_ld_wait();
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            skip[h8 * 4 + p] = fadd2(skip[h8 * 4 + p], relu2(pk(s[2 * p], s[2 * p + 1])));
-          }
+          for (int p = 0; p < 4; ++p) skip[h8 * 4 + p] = fadd2(skip[h8 * 4 + p], relu2(pk(s[2 * p], s[2 * p + 1])));
         }
         if (last) {
           // detect input: ReLU(skip) hi/lo; channels 0-15 -> the u columns, 16-31 -> the g columns
@@ -380,8 +468,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         }
       }
       // ---- detect head epilogue: ReLU(D + b1) -> 32->2 -> max over time ----
-      mbar_wait(&sm.bar_gate[tile], n_gate & 1);
-      ++n_gate;
+      WN_MBAR_WAIT(&sm.bar_det[tile], n_u & 1, 8);
       fence_after_sync();
       float z0 = sm.head.det2_b[0], z1 = sm.head.det2_b[1];
 #pragma unroll
@@ -417,19 +504,16 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       epi_bar_sync();
     }
   } else {
-    // =========================== MMA issuer + weight loader ===========================
-    // Static software-pipelined order with blocking (sleeping) mbarrier waits; per block k:
-    //     G0 R3' G1 R4' G2 R0 G3 R1 G4 R2          (G = gate GEMM, R = res/skip GEMM, ' = block k-1)
-    // i.e. tile i+3's res/skip GEMM is issued half a period after its gate GEMM, which is where the
-    // evenly staggered steady state puts it.  The order also satisfies the hazard rule (header): R_i
-    // follows G_{i+1} of the same block.  All descriptors are a loop-invariant base plus a small
-    // uniform offset, so an issue slot is ~40 uniform-datapath instructions.
-    const uint32_t idesc_gate = make_idesc_f16(128, 32), idesc_rs = make_idesc_f16(128, 48);
+    // =========================== gate-GEMM warp + weight loader ===========================
+    // Issues the gate GEMMs tile after tile, each as soon as the tile's epilogue 2 has arrived.  Because one
+    // thread issues them, they execute back to back in tile order, which staggers the tiles: while tile i+1's
+    // gate GEMM runs, tile i is in epilogue 1 (SFU), tile i-1 in its res/skip GEMM or epilogue 2 (FMA/ALU).
+    // gate(k,i) also needs epilogue 2 of (k-1,i-1) (its taps reach 16 rows into tile i-1): awaited one step earlier.
+    const int tile = 0, q = 0;   // (for the hang report)
+    uint32_t n_gate = 0, n_rs = 0, n_u = 0;
     const uint64_t dU = make_desc(smem_u32(sm.U), WN_PU, 128);                   // U row 0, hi plane
     const uint64_t dWg = make_desc(smem_u32(sm.W[0]), 512, 128);                 // gate B: stage 0, tap 0, hi plane
-    const uint64_t dWr = make_desc(smem_u32(sm.W[0]) + WN_GATE_B, 768, 128);     // res/skip B: stage 0, hi plane
     const uint64_t dBg = make_desc(smem_u32(sm.W[0]) + WN_OFF_GBIAS, 512, 128);  // gate bias B: stage 0
-    const uint64_t dBr = make_desc(smem_u32(sm.W[0]) + WN_OFF_RBIAS, 768, 128);  // res/skip bias B: stage 0
     const uint64_t dH = make_desc(smem_u32(sm.head.det1_B), 512, 128);           // detect B: k-step 0, hi plane
     uint32_t my_groups = 0;
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) ++my_groups;
@@ -439,88 +523,60 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         mbar_arrive_expect_tx(&sm.wfull[n], WN_WBLK);
         bulk_g2s(sm.W[n], P.wblob + (size_t)n * WN_WBLK, WN_WBLK, &sm.wfull[n]);
       }
-    uint32_t nb = 0;          // global block index (24 per group)
-    uint32_t ubase = 0;       // bar_u phases before this group (25 per group), bar_g phases = nb
-    auto issue_rs = [&](const int j, const uint32_t blk, const int kk, const int64_t grp) {
-      if (j == 3) WN_DBG(7, kk, 0);
-      mbar_wait(&sm.bar_g[j], blk & 1);
-      if (j == 3) WN_DBG(7, kk, 1);
-      fence_after_sync();
-      if (elect_one()) {
-        const uint32_t tacc = tmem + j * WN_TMEM_TILE;
-        const uint64_t bh = dWr + (uint64_t)((blk % WN_WST) * (WN_WBLK >> 4)), bl = bh + (uint64_t)(1536 >> 4);
-        mma_f16_ts(tacc, tacc + WN_C_G, bh, idesc_rs, false);
-        if (nsplit == 3) {
-          mma_f16_ts(tacc, tacc + WN_C_G + 8, bh, idesc_rs, true);
-          mma_f16_ts(tacc, tacc + WN_C_G, bl, idesc_rs, true);
-        }
-        mma_f16_ts(tacc, tacc + WN_C_ONE, dBr + (uint64_t)((blk % WN_WST) * (WN_WBLK >> 4)), idesc_rs, true);
-        mma_commit(&sm.bar_rs[j]);
-        if (j == 0) WN_DBG(5, kk, 2);
-        if (j == WN_NT - 1) WN_DBG(5, kk, 3);
-      }
-      __syncwarp();
-      if (j == 3) WN_DBG(7, kk, 2);
-    };
+    uint32_t n_w = 0;         // global block index (24 per group)
+    uint32_t ubase = 0;       // bar_u phases before this group (25 per group)
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ubase += 25) {
-      for (int k = 0; k < 24; ++k, ++nb) {
-        mbar_wait(&sm.wfull[nb % WN_WST], (nb / WN_WST) & 1);
+      for (int k = 0; k < 24; ++k, ++n_w) {
+        WN_MBAR_WAIT(&sm.wfull[n_w % WN_WST], (n_w / WN_WST) & 1, 1);
         const uint32_t d = (uint32_t)P.dil[k];
-        const uint64_t dWk = dWg + (uint64_t)((nb % WN_WST) * (WN_WBLK >> 4));
+        const uint64_t wofs = (uint64_t)((n_w % WN_WST) * (WN_WBLK >> 4));
+        const uint64_t b0 = dWg + wofs, bb = dBg + wofs;
 #pragma unroll
         for (int i = 0; i < WN_NT; ++i) {
           if (i == 1) WN_DBG(6, k, 0);
-          mbar_wait(&sm.bar_u[i], (ubase + k) & 1);
+          WN_MBAR_WAIT(&sm.bar_u[i], (ubase + k) & 1, 2);
           if (i == 1) WN_DBG(6, k, 1);
           fence_after_sync();
           if (elect_one()) {   // one lane issues the whole tile (uniform descriptors, no per-MMA election)
             const uint32_t tacc = tmem + i * WN_TMEM_TILE;
-#pragma unroll
-            for (int tap = 0; tap < 2; ++tap) {
-              const uint64_t ah = dU + (uint64_t)(16 + i * 128 - (2 - tap) * d), al = ah + (uint64_t)((2 * WN_PU) >> 4);
-              const uint64_t bh = dWk + (uint64_t)((tap * 2 * 512) >> 4), bl = bh + (uint64_t)(3072 >> 4);
-              mma_f16_ss(tacc, ah, bh, idesc_gate, tap != 0);
-              if (nsplit == 3) {
-                mma_f16_ss(tacc, al, bh, idesc_gate, true);
-                mma_f16_ss(tacc, ah, bl, idesc_gate, true);
-              }
+            const uint64_t a0 = dU + (uint64_t)(16 + i * 128 - 2 * d), a1 = dU + (uint64_t)(16 + i * 128 - d);
+            const uint64_t lo_a = (uint64_t)((2 * WN_PU) >> 4), lo_b = (uint64_t)(3072 >> 4);
+            mma_f16_ss(tacc, a0, b0, idesc_gate, false);
+            if (nsplit == 3) {
+              mma_f16_ss(tacc, a0 + lo_a, b0, idesc_gate, true);
+              mma_f16_ss(tacc, a0, b0 + lo_b, idesc_gate, true);
             }
-            {
-              const uint64_t bh = dWk + (uint64_t)((2 * 2 * 512) >> 4), bl = bh + (uint64_t)(3072 >> 4);
-              mma_f16_ts(tacc, tacc + WN_C_U, bh, idesc_gate, true);
-              if (nsplit == 3) {
-                mma_f16_ts(tacc, tacc + WN_C_U + 8, bh, idesc_gate, true);
-                mma_f16_ts(tacc, tacc + WN_C_U, bl, idesc_gate, true);
-              }
-              mma_f16_ts(tacc, tacc + WN_C_ONE, dBg + (uint64_t)((nb % WN_WST) * (WN_WBLK >> 4)), idesc_gate, true);
+            mma_f16_ss(tacc, a1, b0 + 64, idesc_gate, true);
+            if (nsplit == 3) {
+              mma_f16_ss(tacc, a1 + lo_a, b0 + 64, idesc_gate, true);
+              mma_f16_ss(tacc, a1, b0 + 64 + lo_b, idesc_gate, true);
             }
+            mma_f16_ts(tacc, tacc + WN_C_U, b0 + 128, idesc_gate, true);
+            if (nsplit == 3) {
+              mma_f16_ts(tacc, tacc + WN_C_U + 8, b0 + 128, idesc_gate, true);
+              mma_f16_ts(tacc, tacc + WN_C_U, b0 + 128 + lo_b, idesc_gate, true);
+            }
+            mma_f16_ts(tacc, tacc + WN_C_ONE, bb, idesc_gate, true);
             mma_commit(&sm.bar_gate[i]);
             if (i == 0) WN_DBG(5, k, 0);
             if (i == WN_NT - 1) WN_DBG(5, k, 1);
           }
           __syncwarp();
           if (i == 1) WN_DBG(6, k, 2);
-          if (i == WN_NT - 1 && nb >= 1 && nb - 1 + WN_WST < total_loads) {
-            // every tile has finished block nb-1 (its epilogue 2 was awaited above): refill that stage
-            const uint32_t nl = nb - 1 + WN_WST;
-            if (lane == 0) {
-              mbar_arrive_expect_tx(&sm.wfull[nl % WN_WST], WN_WBLK);
-              bulk_g2s(sm.W[nl % WN_WST], P.wblob + (size_t)(nl % 24) * WN_WBLK, WN_WBLK, &sm.wfull[nl % WN_WST]);
-            }
-          }
-          if (i < 2) {
-            if (k > 0) issue_rs(i + 3, nb - 1, k - 1, grp);
-          } else {
-            issue_rs(i - 2, nb, k, grp);
+        }
+        // every tile has finished block n_w-1 (its epilogue 2 was awaited above): refill that stage
+        if (n_w >= 1 && n_w - 1 + WN_WST < total_loads) {
+          const uint32_t nl = n_w - 1 + WN_WST;
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&sm.wfull[nl % WN_WST], WN_WBLK);
+            bulk_g2s(sm.W[nl % WN_WST], P.wblob + (size_t)(nl % 24) * WN_WBLK, WN_WBLK, &sm.wfull[nl % WN_WST]);
           }
         }
       }
-      issue_rs(3, nb - 1, 23, grp);
-      issue_rs(4, nb - 1, 23, grp);
       // detect head: D[128,32] = ReLU(skip)[128,32] * W1^T ; k-step 0 from the u columns, k-step 1 from the g columns
 #pragma unroll
       for (int i = 0; i < WN_NT; ++i) {
-        mbar_wait(&sm.bar_u[i], (ubase + 24) & 1);
+        WN_MBAR_WAIT(&sm.bar_u[i], (ubase + 24) & 1, 9);
         fence_after_sync();
         if (elect_one()) {
           const uint32_t tacc = tmem + i * WN_TMEM_TILE;
@@ -534,7 +590,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
               mma_f16_ts(tacc, ta, bl, idesc_gate, true);
             }
           }
-          mma_commit(&sm.bar_gate[i]);
+          mma_commit(&sm.bar_det[i]);
         }
         __syncwarp();
       }
@@ -545,7 +601,6 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
   if (warp == WN_EPI_WARPS) tmem_dealloc(tmem, 512);
 }
 
-// ---- host side: pack the weights ------------------------------------------------------------
 // the gate pre-activations are produced pre-scaled for ex2: tanh half by -2*log2(e), sigmoid half by -log2(e)
 static double gate_scale(int n) { return n < 16 ? -2.8853900817779268 : -1.4426950408889634; }
 
