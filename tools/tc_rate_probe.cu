@@ -16,7 +16,7 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uin
       : "memory");
 }
 
-template <int N, int M, bool TS, int NACC = 2>
+template <int N, int M, bool TS, int NACC = 2, int SHIFT = 0>
 __global__ void rate_kernel(int reps, long long* out) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar;
@@ -29,7 +29,7 @@ __global__ void rate_kernel(int reps, long long* out) {
   const uint32_t tmem = slot;
   if (tid < 32) {
     const uint32_t idesc = make_idesc_f16(M, N);
-    const uint64_t da = make_desc(smem_u32(smem), 656 * 16, 128);
+    const uint64_t da = make_desc(smem_u32(smem) + SHIFT * 16, 656 * 16, 128);   // SHIFT rows: start not 128-byte aligned
     const uint64_t db = make_desc(smem_u32(smem) + 2 * 656 * 16, N * 16, 128);
     long long t0 = clock64();
     if (elect_one()) {
@@ -52,15 +52,15 @@ __global__ void rate_kernel(int reps, long long* out) {
   if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
-template <int N, int M, bool TS, int NACC = 2>
+template <int N, int M, bool TS, int NACC = 2, int SHIFT = 0>
 void run(long long* d) {
-  cudaFuncSetAttribute(rate_kernel<N, M, TS, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 61440);
+  cudaFuncSetAttribute(rate_kernel<N, M, TS, NACC, SHIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 61440);
   long long h[2][2];
   for (int i = 0; i < 2; ++i) {
-    rate_kernel<N, M, TS, NACC><<<1, 128, 61440>>>(i == 0 ? 2 : 10, d);
+    rate_kernel<N, M, TS, NACC, SHIFT><<<1, 128, 61440>>>(i == 0 ? 2 : 10, d);
     if (cudaMemcpy(h[i], d, 16, cudaMemcpyDeviceToHost) != cudaSuccess) { printf("error\n"); exit(1); }
   }
-  printf("M=%3d N=%3d %s n_acc=%d : %.1f clk/MMA (pipe), issue %.1f clk/MMA\n", M, N, TS ? "A=tmem" : "A=smem", NACC,
+  printf("M=%3d N=%3d %s n_acc=%d shift=%d rows : %.1f clk/MMA (pipe), issue %.1f clk/MMA\n", M, N, TS ? "A=tmem" : "A=smem", NACC, SHIFT,
          (double)(h[1][1] - h[0][1]) / (8 * 16), (double)(h[1][0] - h[0][0]) / (8 * 16));
 }
 
@@ -77,5 +77,8 @@ int main() {
   run<48, 128, true, 1>(d); run<48, 128, true, 4>(d);
   run<32, 128, false, 1>(d); run<32, 128, false, 2>(d); run<32, 128, false, 4>(d);
   run<64, 128, false, 1>(d); run<64, 128, true, 1>(d);
+  // A start address shifted by whole rows (16 B each): the dilated taps of the WaveNet
+  run<32, 128, false, 1, 1>(d); run<32, 128, false, 1, 2>(d); run<32, 128, false, 1, 4>(d); run<32, 128, false, 1, 7>(d);
+  run<32, 128, false, 1, 8>(d); run<32, 128, false, 1, 16>(d); run<64, 128, false, 1, 1>(d); run<128, 128, false, 1, 1>(d);
   return 0;
 }

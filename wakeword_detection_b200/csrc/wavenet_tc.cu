@@ -24,8 +24,9 @@
 //
 // GEMM issue: one extra warp issues the gate GEMMs tile after tile (in order, so they run back to back and
 // stagger the tiles: the tensor pipe, the SFU and the FMA/ALU pipes then work on different tiles at the
-// same time); the small res/skip GEMM is issued by the LAST of the tile's four warps to finish epilogue 1
-// (shared-memory arrival counter), i.e. without a round trip through the issuing warp.  Ordering rules:
+// same time); a second extra warp issues the small res/skip GEMMs, so they never queue behind a wait of the
+// gate warp.  Epilogue 2 is split: 2a (residual -> u) releases the next gate GEMM, 2b (skip sum) overlaps it.
+// Ordering rules:
 //   gate(k,i) needs epilogue 2 of (k-1,i) and (k-1,i-1)      (its taps reach 16 rows into tile i-1)
 //   rs(k,i)   needs epilogue 1 of (k,i) and gate(k,i+1) COMPLETE: epilogue 2 of (k,i) overwrites rows that
 //             GEMM reads, and GEMMs issued by different threads have no implicit order.
@@ -46,7 +47,7 @@ constexpr int WN_UROWS = WN_ROWS + 16;        // U buffer has 16 leading zero ro
 constexpr int WN_PU = WN_UROWS * 16;          // bytes per U chunk panel
 constexpr int WN_EPI_WARPS = WN_NT * 4;       // 20
 constexpr int WN_EPI_THREADS = WN_EPI_WARPS * 32;
-constexpr int WN_THREADS = (WN_EPI_WARPS + 1) * 32;   // + the gate-GEMM / loader warp = 672
+constexpr int WN_THREADS = (WN_EPI_WARPS + 2) * 32;   // + the gate-GEMM / loader warp + the res/skip-GEMM warp = 704
 constexpr int WN_GATE_B = 6144, WN_RS_B = 3072;   // gate / res+skip B operands (hi and lo planes)
 constexpr int WN_F32_B = 512;                     // fp32 constants: [80..95] next block's BN scale, [96..111] BN shift
 constexpr int WN_GBIAS_B = 1024, WN_RBIAS_B = 1536;   // bias B operands for the 'ones' GEMM (k0 = hi, k1 = lo)
@@ -54,9 +55,10 @@ constexpr int WN_OFF_F32 = WN_GATE_B + WN_RS_B, WN_OFF_GBIAS = WN_OFF_F32 + WN_F
 constexpr int WN_WBLK = WN_OFF_RBIAS + WN_RBIAS_B;    // 12288 bytes of one block's weight blob
 constexpr int WN_WST = 4;                     // weight ring stages
 constexpr int WN_TMEM_TILE = 96;              // TMEM columns per tile:
-constexpr int WN_C_U = 48;                    //   accumulator 0..47 (gate 0..31, then res/skip 0..47),
-constexpr int WN_C_G = 64;                    //   u hi/lo 48..63, g hi/lo 64..79,
-constexpr int WN_C_ONE = 80;                  //   constant A chunk (k0 = k1 = 1, rest 0) 80..87: adds the biases on the tensor core
+constexpr int WN_C_G = 0;                     //   0..31  gate accumulator; g hi/lo (A of res/skip) overwrites 0..15 once epilogue 1 has read it
+constexpr int WN_C_R = 32;                    //   32..47 res accumulator, 48..79 skip accumulator (detect: 32..63)
+constexpr int WN_C_U = 80;                    //   80..95 u hi/lo (A of the gate's unshifted tap)
+constexpr int WN_C_ONE = WN_NT * WN_TMEM_TILE;   // 480..487: constant A chunk (k0 = k1 = 1, rest 0), shared by all tiles: adds the biases
 
 // resident head blob (floats unless noted)
 struct WnHead {
@@ -76,7 +78,7 @@ struct WnSmem {
   WnHead head;
   uint64_t bar_gate[WN_NT], bar_rs[WN_NT], bar_det[WN_NT];   // GEMM completion (tcgen05.commit) -> the tile's four warps
   uint64_t bar_u[WN_NT];                     // the tile's four warps finished epilogue 2 -> gate warp
-  uint32_t cnt_g[WN_NT];                     // warps that finished epilogue 1 (monotonic): the last one issues the res/skip GEMM
+  uint64_t bar_g[WN_NT];                     // the tile's four warps finished epilogue 1 -> res/skip warp
   uint64_t wfull[WN_WST];
   uint32_t tmem_base;
   int zmax[WN_G][2];
@@ -218,12 +220,12 @@ __device__ __noinline__ void wn_hang(long long* dbg, const uint32_t* cnt_u, cons
     if (atomicCAS(reinterpret_cast<unsigned long long*>(base), 0ull, 1ull) == 0ull) {
       base[1] = id; base[2] = blockIdx.x; base[3] = tile; base[4] = q; base[5] = n_gate; base[6] = n_rs;
       base[7] = n_u; base[8] = n_w;
-      for (int i = 0; i < 5; ++i) { base[9 + i] = cnt_u[i]; base[14 + i] = cnt_g[i]; }
+      if (cnt_u) for (int i = 0; i < 5; ++i) { base[9 + i] = cnt_u[i]; base[14 + i] = cnt_g[i]; }
     }
   }
   asm volatile("exit;");
 }
-#define WN_HANG(id) wn_hang(P.dbg, sm.cnt_g, sm.cnt_g, id, tile, q, n_gate, n_rs, n_u, n_w)
+#define WN_HANG(id) wn_hang(P.dbg, nullptr, nullptr, id, tile, q, n_gate, n_rs, n_u, n_w)
 #define WN_MBAR_WAIT(bar, par, id) do { if (!mbar_try_wait(bar, par)) { uint32_t sp_ = 0; while (!mbar_try_wait(bar, par)) if (++sp_ > WN_SPIN_LIMIT) WN_HANG(id); } } while (0)
 #define WN_WAIT_COUNT(cnt, target, id) do { if (lane == 0) { uint32_t sp_ = 0; while ((int32_t)(ld_acquire_shared(cnt) - (target)) < 0) if (++sp_ > (WN_SPIN_LIMIT << 4)) WN_HANG(id); } __syncwarp(); } while (0)
 #else
@@ -245,10 +247,10 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
   for (int i = tid; i < (int)(sizeof(WnHead) / 16); i += WN_THREADS)
     reinterpret_cast<uint4*>(&sm.head)[i] = reinterpret_cast<const uint4*>(P.head)[i];
   if (tid < WN_G * 2) sm.zmax[tid >> 1][tid & 1] = (int)0xff800000;   // -inf
-  if (tid < WN_NT) sm.cnt_g[tid] = 0;
   if (tid == 0) {
     for (int i = 0; i < WN_NT; ++i) {
-      mbar_init(&sm.bar_u[i], 4); mbar_init(&sm.bar_gate[i], 1); mbar_init(&sm.bar_rs[i], 1); mbar_init(&sm.bar_det[i], 1);
+      mbar_init(&sm.bar_u[i], 4); mbar_init(&sm.bar_g[i], 4); mbar_init(&sm.bar_gate[i], 1); mbar_init(&sm.bar_rs[i], 1);
+      mbar_init(&sm.bar_det[i], 1);
     }
     for (int s = 0; s < WN_WST; ++s) mbar_init(&sm.wfull[s], 1);
     mbar_fence_init();
@@ -271,42 +273,15 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     const uint32_t tbase = tacc + ((uint32_t)(q * 32) << 16);         // ... seen from this warp's lane quadrant
     uint32_t n_gate = 0, n_rs = 0, n_w = 0, n_u = 0;  // completed phases of bar_gate / bar_rs ; global block index ; groups done
     unsigned char* const Urow = sm.U + (16 + o) * 16;
-    const uint64_t dWr = make_desc(smem_u32(sm.W[0]) + WN_GATE_B, 768, 128);
-    const uint64_t dBr = make_desc(smem_u32(sm.W[0]) + WN_OFF_RBIAS, 768, 128);
     {
       uint32_t one[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) one[i] = 0u;
       one[0] = 0x3c003c00u;   // (1.0h, 1.0h)
-      tmem_st16(tbase + WN_C_ONE, one);
+      tmem_st16(tmem + ((uint32_t)(q * 32) << 16) + WN_C_ONE, one);
       tmem_st_wait();
     }
     const u64 ZERO2 = pk(0.f, 0.f), ONE2 = pk(1.f, 1.f);
-
-    // res/skip GEMM of block k, issued by the LAST of the tile's four warps to finish epilogue 1 (all lanes call;
-    // one elected lane issues).  A = g from TMEM, + bias k-step.  Epilogue 2 of this tile will overwrite rows
-    // that gate(k) of tile+1 reads, so that GEMM must have COMPLETED (it is issued by another thread).
-    auto issue_rs = [&](const int k, const uint32_t nb, const int64_t grp) {
-      if (tile == 3) WN_DBG(7, k, 0);
-      if (tile < WN_NT - 1) WN_MBAR_WAIT(&sm.bar_gate[tile + 1], (n_gate - 1) & 1, 3);
-      if (tile == 3) WN_DBG(7, k, 1);
-      const uint64_t wofs = (uint64_t)((nb % WN_WST) * (WN_WBLK >> 4));
-      const uint64_t bh = dWr + wofs, bb = dBr + wofs;
-      fence_after_sync();
-      if (elect_one()) {
-        mma_f16_ts(tacc, tacc + WN_C_G, bh, idesc_rs, false);
-        if (nsplit == 3) {
-          mma_f16_ts(tacc, tacc + WN_C_G + 8, bh, idesc_rs, true);
-          mma_f16_ts(tacc, tacc + WN_C_G, bh + (uint64_t)(1536 >> 4), idesc_rs, true);
-        }
-        mma_f16_ts(tacc, tacc + WN_C_ONE, bb, idesc_rs, true);
-        mma_commit(&sm.bar_rs[tile]);
-      }
-      __syncwarp();
-      if (tile == 0) WN_DBG(5, k, 2);
-      if (tile == WN_NT - 1) WN_DBG(5, k, 3);
-      if (tile == 3) WN_DBG(7, k, 2);
-    };
 
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++n_u) {
       const int64_t b = grp * WN_G + w;
@@ -397,9 +372,10 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         }
         fence_before_sync();
         if (q == 0 && lane == 0) WN_DBG(tile, k, 1);
-        if (arrive_is_last(&sm.cnt_g[tile], lane)) issue_rs(k, n_w, grp);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.bar_g[tile]);
 
-        // ---- epilogue 2: residual + skip, next block's BN ----
+        // ---- epilogue 2a: residual, next block's BN -> u (releases the next gate GEMM) ----
         WN_MBAR_WAIT(&sm.bar_rs[tile], n_rs & 1, 6);
         ++n_rs;
         fence_after_sync();
@@ -410,7 +386,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8) {
             float r[8];
-            tmem_ld8(tbase + h8 * 8, r);
+            tmem_ld8(tbase + WN_C_R + h8 * 8, r);
             tmem_ld_wait();
             const ulonglong2* bm = reinterpret_cast<const ulonglong2*>(wf + 80 + h8 * 8);
             const ulonglong2* ba = reinterpret_cast<const ulonglong2*>(wf + 96 + h8 * 8);
@@ -430,15 +406,23 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             *reinterpret_cast<uint4*>(Urow + 3 * WN_PU) = make_uint4(ur[12], ur[13], ur[14], ur[15]);
           }
           tmem_st16(tbase + WN_C_U, ur);
+          tmem_st_wait();
+          fence_before_sync();
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.bar_u[tile]);
+          if (q == 0 && lane == 0) WN_DBG(tile, k, 3);
         }
+        // ---- epilogue 2b: skip sum (off the critical path: the next gate GEMM is already running) ----
 #pragma unroll
         for (int h8 = 0; h8 < 4; ++h8) {
           float s[8];
-          tmem_ld8(tbase + 16 + h8 * 8, s);
+          tmem_ld8(tbase + WN_C_R + 16 + h8 * 8, s);
           tmem_ld_wait();
 #pragma unroll
           for (int p = 0; p < 4; ++p) skip[h8 * 4 + p] = fadd2(skip[h8 * 4 + p], relu2(pk(s[2 * p], s[2 * p + 1])));
         }
+        fence_before_sync();
         if (last) {
           // detect input: ReLU(skip) hi/lo; channels 0-15 -> the u columns, 16-31 -> the g columns
           uint32_t er[16];
@@ -448,13 +432,12 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
 #pragma unroll
           for (int c = 0; c < 8; ++c) split2(relu2(skip[8 + c]), er[c], er[8 + c]);
           tmem_st16(tbase + WN_C_G, er);
+          tmem_st_wait();
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.bar_u[tile]);
+          if (q == 0 && lane == 0) WN_DBG(tile, k, 3);
         }
-        tmem_st_wait();
-        fence_before_sync();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.bar_u[tile]);
-        if (q == 0 && lane == 0) WN_DBG(tile, k, 3);
       }
 
       if (P.enc_out && valid) {
@@ -474,7 +457,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
 #pragma unroll
       for (int h8 = 0; h8 < 4; ++h8) {
         float d[8];
-        tmem_ld8(tbase + h8 * 8, d);
+        tmem_ld8(tbase + WN_C_R + h8 * 8, d);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -503,7 +486,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       }
       epi_bar_sync();
     }
-  } else {
+  } else if (warp == WN_EPI_WARPS) {
     // =========================== gate-GEMM warp + weight loader ===========================
     // Issues the gate GEMMs tile after tile, each as soon as the tile's epilogue 2 has arrived.  Because one
     // thread issues them, they execute back to back in tile order, which staggers the tiles: while tile i+1's
@@ -556,7 +539,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
               mma_f16_ts(tacc, tacc + WN_C_U + 8, b0 + 128, idesc_gate, true);
               mma_f16_ts(tacc, tacc + WN_C_U, b0 + 128 + lo_b, idesc_gate, true);
             }
-            mma_f16_ts(tacc, tacc + WN_C_ONE, bb, idesc_gate, true);
+            mma_f16_ts(tacc, tmem + WN_C_ONE, bb, idesc_gate, true);
             mma_commit(&sm.bar_gate[i]);
             if (i == 0) WN_DBG(5, k, 0);
             if (i == WN_NT - 1) WN_DBG(5, k, 1);
@@ -584,15 +567,56 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           for (int kk = 0; kk < 2; ++kk) {
             const uint32_t ta = tacc + (kk == 0 ? WN_C_U : WN_C_G);
             const uint64_t bh = dH + (uint64_t)((kk * 2 * 512) >> 4), bl = bh + (uint64_t)(2048 >> 4);
-            mma_f16_ts(tacc, ta, bh, idesc_gate, kk != 0);
+            mma_f16_ts(tacc + WN_C_R, ta, bh, idesc_gate, kk != 0);
             if (nsplit == 3) {
-              mma_f16_ts(tacc, ta + 8, bh, idesc_gate, true);
-              mma_f16_ts(tacc, ta, bl, idesc_gate, true);
+              mma_f16_ts(tacc + WN_C_R, ta + 8, bh, idesc_gate, true);
+              mma_f16_ts(tacc + WN_C_R, ta, bl, idesc_gate, true);
             }
           }
           mma_commit(&sm.bar_det[i]);
         }
         __syncwarp();
+      }
+    }
+  } else {
+    // =========================== res/skip-GEMM warp ===========================
+    // Tile after tile: when the tile's four warps have stored g (epilogue 1), issue its res and skip GEMMs
+    // (A = g from TMEM, + bias k-step).  Epilogue 2a of the tile will then overwrite rows that gate(k) of
+    // tile+1 reads, so that GEMM must have COMPLETED first (it is issued by another thread: no implicit order).
+    const int tile = 1, q = 0;   // (for the hang report)
+    uint32_t n_gate = 0, n_rs = 0, n_u = 0, n_w = 0;
+    const uint64_t dWr = make_desc(smem_u32(sm.W[0]) + WN_GATE_B, 768, 128);     // res/skip B: stage 0, hi plane
+    const uint64_t dBr = make_desc(smem_u32(sm.W[0]) + WN_OFF_RBIAS, 768, 128);  // res/skip bias B: stage 0
+    const uint32_t ones = tmem + WN_C_ONE;
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+      for (int k = 0; k < 24; ++k, ++n_w) {
+        const uint64_t wofs = (uint64_t)((n_w % WN_WST) * (WN_WBLK >> 4));
+        const uint64_t bh = dWr + wofs, bb = dBr + wofs, lo_b = (uint64_t)(1536 >> 4);
+        WN_MBAR_WAIT(&sm.wfull[n_w % WN_WST], (n_w / WN_WST) & 1, 11);   // (observe the weight load ourselves)
+#pragma unroll
+        for (int i = 0; i < WN_NT; ++i) {
+          if (i == 3) WN_DBG(7, k, 0);
+          WN_MBAR_WAIT(&sm.bar_g[i], n_w & 1, 10);
+          if (i < WN_NT - 1) WN_MBAR_WAIT(&sm.bar_gate[i + 1], n_w & 1, 3);
+          if (i == 3) WN_DBG(7, k, 1);
+          fence_after_sync();
+          if (elect_one()) {
+            // res (columns 32..47) and skip (48..79) in one N = 48 GEMM.  One commit: the next gate GEMM overwrites the
+            // g columns, so epilogue 2a must not release it before this GEMM has read them
+            const uint32_t tacc = tmem + i * WN_TMEM_TILE;
+            mma_f16_ts(tacc + WN_C_R, tacc + WN_C_G, bh, idesc_rs, false);
+            if (nsplit == 3) {
+              mma_f16_ts(tacc + WN_C_R, tacc + WN_C_G + 8, bh, idesc_rs, true);
+              mma_f16_ts(tacc + WN_C_R, tacc + WN_C_G, bh + lo_b, idesc_rs, true);
+            }
+            mma_f16_ts(tacc + WN_C_R, ones, bb, idesc_rs, true);
+            mma_commit(&sm.bar_rs[i]);
+            if (i == 0) WN_DBG(5, k, 2);
+            if (i == WN_NT - 1) WN_DBG(5, k, 3);
+          }
+          __syncwarp();
+          if (i == 3) WN_DBG(7, k, 2);
+        }
       }
     }
   }
