@@ -135,6 +135,18 @@ def cpu_reference_rate(models, n_streams, seconds_per_stream, processes):
     return n_streams * seconds_per_stream / 3600.0 / dt, dt
 
 
+def measured_traffic(kernel, S, N):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r1_traffic.json); only valid for the shape it was captured on."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(kernel)
+        if d and d["streams"] == S and abs(d["seconds"] - N / 16000.0) < 1e-9:
+            return int(d["bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def workload_models(workload):
     return {"sweep": ["CRNN", "Wavenet"], "crnn": ["CRNN"], "wavenet": ["Wavenet"], "filter": []}[workload]
 
@@ -145,7 +157,7 @@ def run_reference_arm(args):
         return
     models = workload_models(args.workload) or ["CRNN"]
     cores = os.cpu_count() or 1
-    sec = 6.0 if args.workload != "filter" else 20.0
+    sec = 30.0 if args.workload != "filter" else 300.0
     rates = []
     for i in range(args.warmup + args.steps):
         if args.workload == "filter":
@@ -357,7 +369,7 @@ def main():
         ach = S * nwin[dom] * FLOP_PER_WINDOW[dom] / (per[dom] / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": dom.lower() + " encode+detect", "achieved": ach,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
-                "traffic": None}
+                "traffic": measured_traffic(dom.lower() + " encode+detect", S, N)}
     roof["peak_source"] = pk_src + (" (sustained bf16)" if dom != "filter" else " (copy)")
     extra = {"ms_per_stage": per,
              "filter_GBps": S * F * BYTES_PER_FRAME / (per["filter"] / 1e3) / 1e9,
@@ -373,14 +385,15 @@ def main():
         if not args.no_cpu_baseline:
             cm = models or ["CRNN"]
             if args.workload == "filter":
-                r, dt = cpu_filter_rate(1, 20.0)
+                r, dt = cpu_filter_rate(1, 1800.0)
                 cpu = {"value": r, "unit": "audio-h/s", "cores": 1, "kind": "port",
-                       "sample": "1 stream x 20 s, filter only, numpy restatement, 1 thread (%.1f s)" % dt}
+                       "sample": "1 stream x 1800 s, filter only, numpy restatement, 1 thread (%.1f s)" % dt}
             else:
-                r, dt = cpu_reference_rate(cm, 1, 6.0, 1)
+                sec = 120.0 * (2.0 / len(cm)) if cm else 120.0
+                r, dt = cpu_reference_rate(cm, 1, sec, 1)
                 cpu = {"value": r, "unit": "audio-h/s", "cores": 1, "kind": "port",
-                       "sample": "1 stream x 6 s through %s, numpy restatement of the TFLite graphs, 1 thread (%.1f s)"
-                                 % ("+".join(cm), dt)}
+                       "sample": "1 stream x %.0f s through %s, numpy restatement of the TFLite graphs, 1 thread (%.1f s)"
+                                 % (sec, "+".join(cm), dt)}
         h2d = S * N * 2
         d2h = sum(S * nwin[m] * 4 for m in models) + len(models) * 2 * thr.size * 8
         line = {"metric": "audio_hours_per_sec", "value": value, "unit": "audio-h/s", "n_gpus": world,
