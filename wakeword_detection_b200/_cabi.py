@@ -12,7 +12,7 @@ from typing import Dict, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwwb200.so")
+LIB_PATH = os.environ.get("WWB200_LIB") or os.path.join(_HERE, "libwwb200.so")   # override: A/B builds of the same ABI
 
 WWB_MODEL_NONE, WWB_MODEL_CRNN, WWB_MODEL_WAVENET = -1, 0, 1
 WWB_PCM_I16, WWB_PCM_F32 = 0, 1

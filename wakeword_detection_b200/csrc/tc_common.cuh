@@ -164,6 +164,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
 #pragma unroll 1
   while (!mbar_try_wait(bar, parity)) {
+#ifdef WWB_WAIT_BACKOFF_NS
+    __nanosleep(WWB_WAIT_BACKOFF_NS);
+#endif
     if (++spins > (1u << 24)) __trap();   // surfaces on the host as a launch failure (no printf: its call ABI costs registers)
   }
 }
