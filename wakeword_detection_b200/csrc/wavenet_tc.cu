@@ -62,14 +62,14 @@ constexpr int WN_C_ONE = WN_NT * WN_TMEM_TILE;   // 480..487: constant A chunk (
 
 // resident head blob (floats unless noted)
 struct WnHead {
-  float in_w[40 * 16];      // [k][c]
-  float in_b[16];
   float bn0_mul[16], bn0_add[16];
   float det1_b[32];
   float det2_w[2 * 32];
   float det2_b[2];
   float pad_[2];
   unsigned char det1_B[2 * 4 * 32 * 16];   // hi/lo planes, 4 chunks x 32 rows x 16 B
+  unsigned char in_B[2 * 6 * 16 * 16];     // input 1x1 conv 40(+8 zero)->16: hi/lo planes, 6 chunks x 16 rows x 16 B
+  unsigned char in_bias_B[2 * 16 * 16];    // its bias for the 'ones' k-step: chunk 0 = (hi, lo, 0...), chunk 1 = 0
 };
 
 struct WnSmem {
@@ -79,6 +79,7 @@ struct WnSmem {
   uint64_t bar_gate[WN_NT], bar_rs[WN_NT], bar_det[WN_NT];   // GEMM completion (tcgen05.commit) -> the tile's four warps
   uint64_t bar_u[WN_NT];                     // the tile's four warps finished epilogue 2 -> gate warp
   uint64_t bar_g[WN_NT];                     // the tile's four warps finished epilogue 1 -> res/skip warp
+  uint64_t bar_in_rdy[WN_NT], bar_in[WN_NT]; // input layer: mel rows stored to TMEM -> gate warp ; its GEMM completed
   uint64_t wfull[WN_WST];
   uint32_t tmem_base;
   int zmax[WN_G][2];
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
   if (tid == 0) {
     for (int i = 0; i < WN_NT; ++i) {
       mbar_init(&sm.bar_u[i], 4); mbar_init(&sm.bar_g[i], 4); mbar_init(&sm.bar_gate[i], 1); mbar_init(&sm.bar_rs[i], 1);
-      mbar_init(&sm.bar_det[i], 1);
+      mbar_init(&sm.bar_det[i], 1); mbar_init(&sm.bar_in_rdy[i], 4); mbar_init(&sm.bar_in[i], 1);
     }
     for (int s = 0; s < WN_WST; ++s) mbar_init(&sm.wfull[s], 1);
     mbar_fence_init();
@@ -287,39 +288,50 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       const int64_t b = grp * WN_G + w;
       const bool valid = (w < WN_G) && (t < L) && (b < n_win);
       u64 x[8], skip[16];     // channel pairs
-      // ---- input layer: x = ReLU(in_w * mel + in_b); u0 = BN_0(x) ----
+      // ---- input layer: x = ReLU(in_w * mel + in_b) on the tensor core; u0 = BN_0(x) ----
+      // (as 640 FFMA per row fed by broadcast LDS.128 of the weights it cost ~13 % of the kernel: the loads alone are
+      //  4 shared-memory wavefronts each.)  The row's 40 mel values go to TMEM as three fp16 hi/lo k-chunks (the res/skip
+      //  accumulator columns are free at this point); the gate warp issues D[128,16] = mel * in_w^T (+ bias k-step).
       {
+        const float4* row = reinterpret_cast<const float4*>(win_row(P.wm, valid ? b : 0, valid ? t : 0));
 #pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const u64*>(sm.head.in_b + 2 * c);
-        if (valid) {
-          const float4* row = reinterpret_cast<const float4*>(win_row(P.wm, b, t));
+        for (int c = 0; c < 3; ++c) {
+          uint32_t ar[16];
 #pragma unroll
-          for (int k4 = 0; k4 < 10; ++k4) {
-            const float4 m = __ldg(row + k4);
-            const float mm[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(sm.head.in_w + (k4 * 4 + j) * 16);
-              const u64 m2 = pk(mm[j], mm[j]);
-#pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4) {
-                const ulonglong2 wv = wr[c4];
-                x[c4 * 2] = ffma2(wv.x, m2, x[c4 * 2]);
-                x[c4 * 2 + 1] = ffma2(wv.y, m2, x[c4 * 2 + 1]);
-              }
+          for (int j4 = 0; j4 < 4; ++j4) {
+            if (c * 4 + j4 < 10) {
+              float4 m = __ldg(row + c * 4 + j4);
+              if (!valid) m = make_float4(0.f, 0.f, 0.f, 0.f);
+              split2(pk(m.x, m.y), ar[2 * j4], ar[8 + 2 * j4]);
+              split2(pk(m.z, m.w), ar[2 * j4 + 1], ar[8 + 2 * j4 + 1]);
+            } else {
+              ar[2 * j4] = ar[2 * j4 + 1] = ar[8 + 2 * j4] = ar[8 + 2 * j4 + 1] = 0u;
             }
           }
+          tmem_st16(tbase + WN_C_R + 16 * c, ar);
         }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = relu2(x[c]);
+        tmem_st_wait();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.bar_in_rdy[tile]);
 #pragma unroll
         for (int n = 0; n < 16; ++n) skip[n] = ZERO2;
+        WN_MBAR_WAIT(&sm.bar_in[tile], n_u & 1, 12);
+        fence_after_sync();
         uint32_t ur[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const u64 u = ffma2(x[c], *reinterpret_cast<const u64*>(sm.head.bn0_mul + 2 * c),
-                              *reinterpret_cast<const u64*>(sm.head.bn0_add + 2 * c));
-          split2(u, ur[c], ur[8 + c]);
+        for (int h8 = 0; h8 < 2; ++h8) {
+          float r[8];
+          tmem_ld8(tbase + WN_C_G + h8 * 8, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int c = h8 * 4 + p;
+            x[c] = relu2(pk(r[2 * p], r[2 * p + 1]));
+            const u64 u = ffma2(x[c], *reinterpret_cast<const u64*>(sm.head.bn0_mul + 2 * c),
+                                *reinterpret_cast<const u64*>(sm.head.bn0_add + 2 * c));
+            split2(u, ur[c], ur[8 + c]);
+          }
         }
         if (valid) {
           *reinterpret_cast<uint4*>(Urow) = make_uint4(ur[0], ur[1], ur[2], ur[3]);
@@ -508,7 +520,33 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       }
     uint32_t n_w = 0;         // global block index (24 per group)
     uint32_t ubase = 0;       // bar_u phases before this group (25 per group)
-    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ubase += 25) {
+    const uint64_t dIn = make_desc(smem_u32(sm.head.in_B), 256, 128);            // input conv B: k-step 0, hi plane
+    const uint64_t dInB = make_desc(smem_u32(sm.head.in_bias_B), 256, 128);      // input conv bias B
+    const uint32_t idesc_in = make_idesc_f16(128, 16);
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ubase += 25, ++n_u) {
+      // input layer: D[128,16] (gate accumulator columns) = mel[128,48] * in_w^T + bias; A = the three k-chunks the
+      // tile's threads stored into the res/skip accumulator columns
+#pragma unroll
+      for (int i = 0; i < WN_NT; ++i) {
+        WN_MBAR_WAIT(&sm.bar_in_rdy[i], n_u & 1, 13);
+        fence_after_sync();
+        if (elect_one()) {
+          const uint32_t tacc = tmem + i * WN_TMEM_TILE;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const uint32_t ta = tacc + WN_C_R + 16 * c;
+            const uint64_t bh = dIn + (uint64_t)((c * 512) >> 4), bl = bh + (uint64_t)(1536 >> 4);
+            mma_f16_ts(tacc + WN_C_G, ta, bh, idesc_in, c != 0);
+            if (nsplit == 3) {
+              mma_f16_ts(tacc + WN_C_G, ta + 8, bh, idesc_in, true);
+              mma_f16_ts(tacc + WN_C_G, ta, bl, idesc_in, true);
+            }
+          }
+          mma_f16_ts(tacc + WN_C_G, tmem + WN_C_ONE, dInB, idesc_in, true);
+          mma_commit(&sm.bar_in[i]);
+        }
+        __syncwarp();
+      }
       for (int k = 0; k < 24; ++k, ++n_w) {
         WN_MBAR_WAIT(&sm.wfull[n_w % WN_WST], (n_w / WN_WST) & 1, 1);
         const uint32_t d = (uint32_t)P.dil[k];
@@ -678,13 +716,21 @@ std::vector<unsigned char> wavenet_pack_head(const float* in_w_kc, const float* 
                                              const float* det2_w, const float* det2_b) {
   std::vector<unsigned char> out(sizeof(WnHead), 0);
   WnHead* h = reinterpret_cast<WnHead*>(out.data());
-  memcpy(h->in_w, in_w_kc, sizeof(h->in_w));
-  memcpy(h->in_b, in_b, sizeof(h->in_b));
   memcpy(h->bn0_mul, bn_mul0, sizeof(h->bn0_mul));
   memcpy(h->bn0_add, bn_add0, sizeof(h->bn0_add));
   memcpy(h->det1_b, det1_b, sizeof(h->det1_b));
   memcpy(h->det2_w, det2_w, sizeof(h->det2_w));
   memcpy(h->det2_b, det2_b, sizeof(h->det2_b));
+  // input conv B operand: row n = output channel, k = mel bin (40, zero-padded to 48)
+  const size_t ioff = offsetof(WnHead, in_B);
+  for (int n = 0; n < 16; ++n)
+    for (int k = 0; k < 40; ++k) {
+      const int c = k / 8, e = k % 8;
+      const size_t off = ioff + ((size_t)c * 16 + n) * 16 + e * 2;
+      put_split(out, off, off + 1536, in_w_kc[k * 16 + n], true);
+    }
+  const size_t iboff = offsetof(WnHead, in_bias_B);
+  for (int n = 0; n < 16; ++n) put_split(out, iboff + (size_t)n * 16, iboff + (size_t)n * 16 + 2, in_b[n], true);
   const size_t boff = offsetof(WnHead, det1_B);
   for (int n = 0; n < 32; ++n)
     for (int k = 0; k < 32; ++k) {
