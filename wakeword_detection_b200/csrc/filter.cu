@@ -51,6 +51,11 @@ struct __align__(16) FilterSmem {
   float hann[kFFT];
   float2 tw512[256];
   float partial[FR_TILE][MAX_SEG];
+  // mel tables (batch kernel): segment -> taps, band -> segments
+  float seg_w[MAX_SEG][8];             // every segment padded to 8 taps (weight 0, bin 0): fma(0, x, acc) == acc
+  unsigned short seg_bin[MAX_SEG][8];
+  int band_seg0[kMel + 1];
+  float band_bias[kMel];
 };
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -183,6 +188,39 @@ __device__ __forceinline__ void mel_phase(FilterSmem& sm, const MelParams& P, in
   }
 }
 
+// Same arithmetic as mel_phase (per segment an fma chain from 0, segments added in order, bias, floor, log), i.e.
+// bit-identical to mel_phase / mel_from_mag_kernel, but with the tables in shared memory and every segment padded
+// to exactly 8 taps, so the 8 (weight, bin, magnitude) loads of an item are issued together instead of one
+// dependent load chain per tap.  Contains one barrier.
+__device__ __forceinline__ void mel_fast(FilterSmem& sm, const MelParams& P, int n_seg, int nf, float* __restrict__ out) {
+  for (int it = threadIdx.x; it < n_seg * FR_TILE; it += blockDim.x) {
+    const int f = it & (FR_TILE - 1), seg = it / FR_TILE;
+    if (f < nf) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&sm.seg_w[seg][0]), w1 = *reinterpret_cast<const float4*>(&sm.seg_w[seg][4]);
+      const uint4 bb = *reinterpret_cast<const uint4*>(&sm.seg_bin[seg][0]);
+      const float* row = sm.mag[f];
+      const float m0 = row[bb.x & 0xffff], m1 = row[bb.x >> 16], m2 = row[bb.y & 0xffff], m3 = row[bb.y >> 16];
+      const float m4 = row[bb.z & 0xffff], m5 = row[bb.z >> 16], m6 = row[bb.w & 0xffff], m7 = row[bb.w >> 16];
+      float acc = 0.f;
+      acc = fmaf(w0.x, m0, acc); acc = fmaf(w0.y, m1, acc); acc = fmaf(w0.z, m2, acc); acc = fmaf(w0.w, m3, acc);
+      acc = fmaf(w1.x, m4, acc); acc = fmaf(w1.y, m5, acc); acc = fmaf(w1.z, m6, acc); acc = fmaf(w1.w, m7, acc);
+      sm.partial[f][seg] = acc;
+    }
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < nf * kMel; o += blockDim.x) {
+    const int f = o / kMel, band = o - f * kMel;
+    const int s0 = sm.band_seg0[band], s1 = sm.band_seg0[band + 1];
+    float acc = 0.f;
+    for (int s = s0; s < s1; ++s) acc += sm.partial[f][s];
+    acc += sm.band_bias[band];
+    acc = fmaxf(acc, P.mel_floor);
+    float y = logf(acc);
+    y = __fsub_rn(y, P.mel_log_offset);
+    out[o] = __fmul_rn(y, P.mel_scale);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(F_THREADS, 2) filter_kernel(const FilterParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -199,18 +237,63 @@ __global__ void __launch_bounds__(F_THREADS, 2) filter_kernel(const FilterParams
   for (int k2 = 0; k2 < 16; ++k2) twj[k2] = P.tw256[(j * k2) & 255];
   __syncthreads();
 
+  {
+    const MelTables& mt = P.mp.mt;
+    for (int i = tid; i < mt.n_seg * 8; i += F_THREADS) {
+      const int seg = i >> 3, t = i & 7;
+      const bool in = t < mt.seg_count[seg];
+      sm.seg_w[seg][t] = in ? mt.tap_w[mt.seg_first[seg] + t] : 0.0f;
+      sm.seg_bin[seg][t] = in ? (unsigned short)mt.tap_bin[mt.seg_first[seg] + t] : (unsigned short)0;
+    }
+    for (int i = tid; i <= kMel; i += F_THREADS) sm.band_seg0[i] = mt.band_seg0[i];
+    for (int i = tid; i < kMel; i += F_THREADS) sm.band_bias[i] = mt.bias[i];
+  }
+  __syncthreads();
+
   const T* pcm = reinterpret_cast<const T*>(P.pcm);
+  // Fast path (int16, 8-byte aligned rows, no pre-emphasis = the reference's default): the next tile's PCM is
+  // prefetched into registers while the current tile's spectra are computed, and a tile costs two barriers.
+  const bool fast = sizeof(T) == 2 && P.a == 0.0f && (reinterpret_cast<uintptr_t>(pcm) & 7) == 0 && (P.pitch & 3) == 0;
+  constexpr int NPRE = (TILE_SAMPLES / 4 + F_THREADS - 1) / F_THREADS;   // 3 uint2 per thread
+  uint2 pre[NPRE];
+  auto tile_geom = [&](int64_t tile, int64_t& s_out, int64_t& f0_out, int& nf_out) {
+    s_out = tile / P.tiles_per_stream;
+    f0_out = (tile - s_out * P.tiles_per_stream) * FR_TILE;
+    nf_out = (int)min((int64_t)FR_TILE, P.n_frames - f0_out);
+  };
+  auto prefetch = [&](int64_t tile) {
+    int64_t s, f0; int nf;
+    tile_geom(tile, s, f0, nf);
+    const int ns = (nf - 1) * kHop + kFFT;
+    const uint2* v4 = reinterpret_cast<const uint2*>(reinterpret_cast<const int16_t*>(P.pcm) + s * P.pitch + f0 * kHop);
+#pragma unroll
+    for (int c = 0; c < NPRE; ++c) {
+      const int i = tid + c * F_THREADS;
+      pre[c] = (i < ns / 4) ? __ldg(v4 + i) : make_uint2(0u, 0u);
+    }
+  };
+  if (fast && (int64_t)blockIdx.x < P.n_tiles) prefetch(blockIdx.x);
+
   for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-    const int64_t s = tile / P.tiles_per_stream;
-    const int fb = (int)(tile - s * P.tiles_per_stream);
-    const int64_t f0 = (int64_t)fb * FR_TILE;
-    const int nf = (int)min((int64_t)FR_TILE, P.n_frames - f0);
+    int64_t s, f0; int nf;
+    tile_geom(tile, s, f0, nf);
     const int ns = (nf - 1) * kHop + kFFT;
     const T* row = pcm + s * P.pitch;
     const int64_t start = f0 * kHop;
 
     // stage samples (converted to float) in shared memory
-    if (sizeof(T) == 2 && ((reinterpret_cast<uintptr_t>(row + start) & 7) == 0)) {
+    if (fast) {
+#pragma unroll
+      for (int c = 0; c < NPRE; ++c) {
+        const int i = tid + c * F_THREADS;
+        if (i < ns / 4) {
+          const uint2 r = pre[c];
+          *reinterpret_cast<float4*>(&sm.samples[4 * i]) =
+              make_float4(pcm_to_float((int16_t)(r.x & 0xffff)), pcm_to_float((int16_t)(r.x >> 16)),
+                          pcm_to_float((int16_t)(r.y & 0xffff)), pcm_to_float((int16_t)(r.y >> 16)));
+        }
+      }
+    } else if (sizeof(T) == 2 && ((reinterpret_cast<uintptr_t>(row + start) & 7) == 0)) {
       const uint2* v4 = reinterpret_cast<const uint2*>(row + start);
       for (int i = tid; i < ns / 4; i += F_THREADS) {
         uint2 r = __ldg(v4 + i);
@@ -236,12 +319,14 @@ __global__ void __launch_bounds__(F_THREADS, 2) filter_kernel(const FilterParams
       for (int i = tid; i < ns; i += F_THREADS, ++c) sm.samples[i] = y[c];
     }
     __syncthreads();
+    if (fast && tile + gridDim.x < P.n_tiles) prefetch(tile + gridDim.x);   // latency hidden behind the FFTs
 
     if (g < nf)
       frame_spectrum(sm.samples + g * kHop, sm.hann, sm.tw512, twj, sm.xch[g], sm.mag[g], j, group_mask);
     __syncthreads();
-    mel_phase(sm, P.mp, nf, P.mel + (s * P.n_frames + f0) * kMel);
-    __syncthreads();
+    // (no barrier after this: the next store goes to `samples`, which nobody reads any more, and the next
+    //  spectra overwrite `mag` / the next mel phase `partial` only after the barrier that follows that store)
+    mel_fast(sm, P.mp, P.mp.mt.n_seg, nf, P.mel + (s * P.n_frames + f0) * kMel);
   }
 }
 
