@@ -47,7 +47,8 @@ constexpr int CA_W1_SLOTS = 2;
 constexpr int CA_CR = 3;                          // conv accumulator / A1 slice ring depth
 constexpr int CA_CW_PLANE = 16 * 32 * 16;         // conv weights: 16 k-chunks x 32 channels
 constexpr int CA_EPI_WARPS = 4, CA_PROD_WARPS = 4;                  // producer warps per set; two sets alternate groups
-constexpr int CA_THREADS = (CA_EPI_WARPS + 2 + 2 * CA_PROD_WARPS) * 32;   // 448
+constexpr int CA_ROLE_WARPS = 3;                  // conv-GEMM issuer, W1 loader, projection-GEMM issuer
+constexpr int CA_THREADS = (CA_EPI_WARPS + CA_ROLE_WARPS + 2 * CA_PROD_WARPS) * 32;   // 480
 
 struct CaSmem {
   unsigned char xp[2 * CA_XP_PLANE];
@@ -202,60 +203,25 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
       fence_before_sync();
     }
   } else if (warp == CA_EPI_WARPS) {
-    // =========================== MMA issuer ===========================
+    // =========================== conv-GEMM issuer ===========================
     // All MMAs of one step are issued by ONE elected lane inside a single branch (descriptors are
     // built there with integer adds); per-MMA election costs ~20 extra instructions on this warp,
     // which made the issue rate, not the tensor pipe, the limiter (profiles/r1_crnn_front.md).
-    const uint32_t idesc_c = make_idesc_f16(128, 32), idesc_p = make_idesc_f16(128, 192);
+    // The projection GEMMs have their own issuing warp: with one warp for both, the ~5 barrier waits per
+    // slice (each >= 100 clk even when already complete) plus two blocking issue phases made the issuer
+    // the bottleneck at ~2500 clk per slice against 1575 clk of tensor-pipe work (tools/ca_timeline.py).
+    const uint32_t idesc_c = make_idesc_f16(128, 32);
     const uint32_t uXP = smem_u32(sm.xp), uCW = smem_u32(sm.cw);
     const int nsplit = P.nsplit;
-    uint32_t tcount = 0, w1cnt = 0;
-    auto inproj = [&](uint32_t ci, int f, uint32_t pacc) {
-      const int cb = ci % CA_CR;
-      const int sl = w1cnt % CA_W1_SLOTS;
-      CA_DBG(f, 4);
-      mbar_wait(&sm.a1_full[cb], (ci / CA_CR) & 1);
-      CA_DBG(f, 5);
-      mbar_wait(&sm.w1_full[sl], (w1cnt / CA_W1_SLOTS) & 1);
-      CA_DBG(f, 6);
-      fence_after_sync();
-      if (elect_one()) {
-        const uint64_t da = make_desc(smem_u32(sm.a1[cb]), 2048, 128);
-        const uint64_t db = make_desc(smem_u32(sm.w1[sl]), 3072, 128);
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          const uint64_t dah = da + (uint64_t)(kk * (4096 >> 4)), dal = dah + (uint64_t)(CA_A1_PLANE >> 4);
-          const uint64_t dbh = db + (uint64_t)(kk * (6144 >> 4)), dbl = dbh + (uint64_t)((CA_W1_SLICE / 2) >> 4);
-          mma_f16_ss(pacc, dah, dbh, idesc_p, (f | kk) != 0);
-          if (nsplit == 3) {
-            mma_f16_ss(pacc, dal, dbh, idesc_p, true);
-            mma_f16_ss(pacc, dah, dbl, idesc_p, true);
-          }
-        }
-        mma_commit(&sm.a1_empty[cb]);
-        mma_commit(&sm.w1_empty[sl]);
-      }
-      __syncwarp();
-      CA_DBG(f, 7);
-      ++w1cnt;
-    };
+    uint32_t tcount = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-      const int pb = tcount & 1;
-      const uint32_t pacc = tmem + TM_PACC + pb * 192;
       const uint32_t gbase = tcount * CA_GROUPS;
       int groups_ready = 0;
       for (int f = 0; f < CA_F; ++f) {
         const uint32_t ci = tcount * CA_F + f;
         const int cb = ci % CA_CR;
-        // The projection runs two slices behind the conv, so the epilogue of a slice has a whole
-        // conv + projection period to turn the accumulator into the next A operand.  Waiting for
-        // a1_full(ci-2) here also proves that conv accumulator ci%3 (last used by slice ci-3, whose
-        // epilogue finished before that of ci-2) is free again.
-        if (f == 2) {
-          mbar_wait(&sm.pacc_empty[pb], ((tcount >> 1) & 1) ^ 1);
-          fence_after_sync();
-        }
-        if (f >= 2) inproj(ci - 2, f - 2, pacc);
+        // conv accumulator ci % 3 was last used by slice ci-3: its epilogue has read it once a1_full(ci-3) completed
+        if (ci >= (uint32_t)CA_CR) mbar_wait(&sm.a1_full[cb], (((ci - CA_CR) / CA_CR) & 1));
         const int g_hi = (2 * f + 12) >> 3;
         CA_DBG(f, 0);
         for (; groups_ready <= g_hi; ++groups_ready) {
@@ -294,10 +260,48 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         __syncwarp();
         CA_DBG(f, 3);
       }
-      inproj(tcount * CA_F + CA_F - 2, CA_F - 2, pacc);
-      inproj(tcount * CA_F + CA_F - 1, CA_F - 1, pacc);
-      if (elect_one()) mma_commit(&sm.pacc_full[pb]);
-      __syncwarp();
+    }
+  } else if (warp == CA_EPI_WARPS + 2) {
+    // =========================== projection-GEMM issuer ===========================
+    // slice f of the GRU-1 input projection: pacc[128,192] += A1_f[128,32] . W1_f^T as soon as the epilogue warps have
+    // turned conv accumulator f into the fp16 hi/lo operand and the W1 slice has landed
+    const uint32_t idesc_p = make_idesc_f16(128, 192);
+    const int nsplit = P.nsplit;
+    uint32_t tcount = 0, w1cnt = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const int pb = tcount & 1;
+      const uint32_t pacc = tmem + TM_PACC + pb * 192;
+      mbar_wait(&sm.pacc_empty[pb], ((tcount >> 1) & 1) ^ 1);
+      for (int f = 0; f < CA_F; ++f, ++w1cnt) {
+        const uint32_t ci = tcount * CA_F + f;
+        const int cb = ci % CA_CR;
+        const int sl = w1cnt % CA_W1_SLOTS;
+        CA_DBG(f, 4);
+        mbar_wait(&sm.a1_full[cb], (ci / CA_CR) & 1);
+        CA_DBG(f, 5);
+        mbar_wait(&sm.w1_full[sl], (w1cnt / CA_W1_SLOTS) & 1);
+        CA_DBG(f, 6);
+        fence_after_sync();
+        if (elect_one()) {
+          const uint64_t da = make_desc(smem_u32(sm.a1[cb]), 2048, 128);
+          const uint64_t db = make_desc(smem_u32(sm.w1[sl]), 3072, 128);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint64_t dah = da + (uint64_t)(kk * (4096 >> 4)), dal = dah + (uint64_t)(CA_A1_PLANE >> 4);
+            const uint64_t dbh = db + (uint64_t)(kk * (6144 >> 4)), dbl = dbh + (uint64_t)((CA_W1_SLICE / 2) >> 4);
+            mma_f16_ss(pacc, dah, dbh, idesc_p, (f | kk) != 0);
+            if (nsplit == 3) {
+              mma_f16_ss(pacc, dal, dbh, idesc_p, true);
+              mma_f16_ss(pacc, dah, dbl, idesc_p, true);
+            }
+          }
+          mma_commit(&sm.a1_empty[cb]);
+          mma_commit(&sm.w1_empty[sl]);
+          if (f == CA_F - 1) mma_commit(&sm.pacc_full[pb]);
+        }
+        __syncwarp();
+        CA_DBG(f, 7);
+      }
     }
   } else if (warp == CA_EPI_WARPS + 1) {
     // =========================== W1 slice loader ===========================
@@ -313,8 +317,8 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
     }
   } else {
     // =========================== XP producers ===========================
-    const int pset = (warp - (CA_EPI_WARPS + 2)) / CA_PROD_WARPS;       // this set fills the groups with gg % 2 == pset
-    const int task = tid - (CA_EPI_WARPS + 2 + pset * CA_PROD_WARPS) * 32;   // 0..127; element e = task
+    const int pset = (warp - (CA_EPI_WARPS + CA_ROLE_WARPS)) / CA_PROD_WARPS;       // this set fills the groups with gg % 2 == pset
+    const int task = tid - (CA_EPI_WARPS + CA_ROLE_WARPS + pset * CA_PROD_WARPS) * 32;   // 0..127; element e = task
     const int wl = task / CA_TP, c = task - wl * CA_TP;  // window in tile, time chunk (frames 8c-6 .. 8c+1)
     const bool has_task = task < CA_WPT * CA_TP;
     const int L = P.L;
