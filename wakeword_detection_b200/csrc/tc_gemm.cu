@@ -59,43 +59,62 @@ tc_gemm_bias_kernel(const float* __restrict__ A, const unsigned char* __restrict
 
   if (warp < G_PRODUCERS) {
     // ---------------- A producers ----------------
+    // Software-pipelined: the global loads of step it+1 are in flight while step it is converted and stored,
+    // and they are issued BEFORE waiting for the shared-memory slot (the kernel is HBM-bound for K = 64:
+    // 128 KB of traffic against 1260 clk of tensor work per tile; exposed load latency was 71 % of its stalls).
     uint32_t it = 0;
     const int r8 = lane & 7, cq = lane >> 3;          // row within an 8-row group, chunk 0..3
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t row0 = tile * 128 + warp * 16;
-      for (int ks = 0; ks < n_ks; ++ks, ++it) {
-        const int s = it % G_STAGES;
-        mbar_wait(&sm.empty[s], ((it / G_STAGES) & 1) ^ 1);
-        unsigned char* hi = sm.a[s];
-        unsigned char* lo = sm.a[s] + G_CH * 128 * 16;
+    const int64_t my_tiles = n_tiles > (int64_t)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_tiles * n_ks;
+    float4 cur[4][2], nxt[4][2];
+    auto load = [&](int64_t step, float4 (&v)[4][2]) {
+      const int64_t tile = blockIdx.x + (step / n_ks) * gridDim.x;
+      const int ks = (int)(step % n_ks);
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
+      for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int r = warp * 16 + rr * 8 + r8;     // row within the tile
-            const int c = cc * 4 + cq;
-            const int64_t grow = tile * 128 + r;
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            if (grow < M) {
-              const float4* src = reinterpret_cast<const float4*>(A + grow * K + ks * G_KS + c * 8);
-              v0 = __ldg(src);
-              v1 = __ldg(src + 1);
-            }
-            const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            __half h[8], l[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) split_f16(x[i], h[i], l[i]);
-            uint4 ph = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
-            uint4 pl = make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7]));
-            *reinterpret_cast<uint4*>(hi + (c * 128 + r) * 16) = ph;
-            *reinterpret_cast<uint4*>(lo + (c * 128 + r) * 16) = pl;
+        for (int cc = 0; cc < 2; ++cc) {
+          const int r = warp * 16 + rr * 8 + r8;
+          const int c = cc * 4 + cq;
+          const int64_t grow = tile * 128 + r;
+          v[rr * 2 + cc][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+          v[rr * 2 + cc][1] = v[rr * 2 + cc][0];
+          if (grow < M) {
+            const float4* src = reinterpret_cast<const float4*>(A + grow * K + ks * G_KS + c * 8);
+            v[rr * 2 + cc][0] = __ldg(src);
+            v[rr * 2 + cc][1] = __ldg(src + 1);
           }
         }
-        (void)row0;
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.full[s]);
+    };
+    if (total > 0) load(0, cur);
+    for (int64_t step = 0; step < total; ++step, ++it) {
+      if (step + 1 < total) load(step + 1, nxt);
+      const int s = it % G_STAGES;
+      mbar_wait(&sm.empty[s], ((it / G_STAGES) & 1) ^ 1);
+      unsigned char* hi = sm.a[s];
+      unsigned char* lo = sm.a[s] + G_CH * 128 * 16;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int r = warp * 16 + rr * 8 + r8;     // row within the tile
+          const int c = cc * 4 + cq;
+          const float4 v0 = cur[rr * 2 + cc][0], v1 = cur[rr * 2 + cc][1];
+          const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          __half h[8], l[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split_f16(x[i], h[i], l[i]);
+          uint4 ph = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+          uint4 pl = make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7]));
+          *reinterpret_cast<uint4*>(hi + (c * 128 + r) * 16) = ph;
+          *reinterpret_cast<uint4*>(lo + (c * 128 + r) * 16) = pl;
+        }
       }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.full[s]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { cur[i][0] = nxt[i][0]; cur[i][1] = nxt[i][1]; }
     }
   } else if (warp == G_PRODUCERS) {
     // ---------------- MMA issuer ----------------
