@@ -95,10 +95,10 @@ struct WnTcParams {
   float* enc_out;
   float* det_out;
   float* post;
-  long long* dbg;   // optional timeline dump (block 0, second group): [8 roles][24 blocks][4 events]
+  long long* dbg;   // optional timeline dump (block 0, second group): [8 roles][2 groups x 24 blocks][4 events]
 };
 
-#define WN_DBG(role, k, ev) do { if (P.dbg && blockIdx.x == 0 && grp == (int64_t)gridDim.x) P.dbg[((role) * 24 + (k)) * 4 + (ev)] = clock64(); } while (0)
+#define WN_DBG(role, k, ev) do { if (P.dbg && blockIdx.x == 0 && (grp == (int64_t)gridDim.x || grp == 2 * (int64_t)gridDim.x)) P.dbg[((role) * 48 + (k) + (grp == (int64_t)gridDim.x ? 0 : 24)) * 4 + (ev)] = clock64(); } while (0)
 
 typedef unsigned long long u64;
 
@@ -217,7 +217,7 @@ __device__ __forceinline__ void wait_count(const uint32_t* cnt, uint32_t target,
 __device__ __noinline__ void wn_hang(long long* dbg, const uint32_t* cnt_u, const uint32_t* cnt_g, int id, int tile, int q,
                                      uint32_t n_gate, uint32_t n_rs, uint32_t n_u, uint32_t n_w) {
   if (dbg) {
-    long long* base = dbg + 8 * 24 * 4;
+    long long* base = dbg + 8 * 48 * 4;
     if (atomicCAS(reinterpret_cast<unsigned long long*>(base), 0ull, 1ull) == 0ull) {
       base[1] = id; base[2] = blockIdx.x; base[3] = tile; base[4] = q; base[5] = n_gate; base[6] = n_rs;
       base[7] = n_u; base[8] = n_w;
