@@ -368,13 +368,16 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             for (int p = 0; p < 4; ++p) {
               // accumulators arrive as a2 = -2*log2(e)*(a + b_t), b2 = -log2(e)*(b + b_s) (scaled weights, bias GEMM)
               const float a0 = at[2 * p], a1 = at[2 * p + 1], b0 = as[2 * p], b1 = as[2 * p + 1];
-              // only e^(-2a) can make the quotient inf/inf, so only it is clamped (tanh is +-1 to 1e-13 there)
-              const float ea0 = ex2_approx(fminf(a0, 43.f)), ea1 = ex2_approx(fminf(a1, 43.f));
-              const float eb0 = ex2_approx(b0), eb1 = ex2_approx(b1);   // e^(-b); inf -> rcp(inf) = 0 -> g = 0
+              // exponents clamped at 30: tanh is -1 and sigmoid 0 to 1e-9 beyond, and both denominators stay below
+              // 2^61, so ONE reciprocal serves the pair of channels (1/d0 = d1/(d0 d1)): 5 SFU ops per pair instead
+              // of 6 - the SFU queue is what stretches this epilogue (profiles/r1_notes.md)
+              const float ea0 = ex2_approx(fminf(a0, 30.f)), ea1 = ex2_approx(fminf(a1, 30.f));
+              const float eb0 = ex2_approx(fminf(b0, 30.f)), eb1 = ex2_approx(fminf(b1, 30.f));
               const u64 tt = fadd2(pk(eb0, eb1), ONE2);
               float d0, d1;
               upk(ffma2(pk(ea0, ea1), tt, tt), d0, d1);                 // (1 + e^-2a)(1 + e^-b)
-              const float r0 = rcp_approx(d0), r1 = rcp_approx(d1);
+              const float rp = rcp_approx(d0 * d1);
+              const float r0 = rp * d1, r1 = rp * d0;
               const u64 g = pk(fmaf(-ea0, r0, r0), fmaf(-ea1, r1, r1)); // tanh(a) * sigmoid(b)
               split2(g, gr[h8 * 4 + p], gr[8 + h8 * 4 + p]);
             }
