@@ -269,6 +269,14 @@ def main():
     stage_ms = {"filter": 0.0, **{m: 0.0 for m in models}, "counts": 0.0}
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
+    def counts():
+        counters = []
+        for m in models:
+            seg = np.arange(S + 1, dtype=np.int64) * nwin[m]
+            counters.append(engines[m].eval_counts(post[m], seg, thr, "far_edges"))
+            counters.append(engines[m].eval_counts(post[m], seg, thr, "frr_max"))
+        return counters
+
     def step(src, timed_stages=None):
         marks = [ev()]
         marks[0].record()
@@ -312,9 +320,27 @@ def main():
         if world > 1 and c:
             wdist.all_reduce_counters(*c)
 
+    # End to end: the streams are pushed through in E2E_CHUNKS slices; the host->device copy of slice i+1 (copy stream)
+    # overlaps filter -> encode -> detect of slice i (compute stream), as a caller feeding host buffers would do it.
+    E2E_CHUNKS = 4 if S % 4 == 0 and S >= 8 else 1
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event() for _ in range(E2E_CHUNKS)]
+
     def e2e_step():
-        pcm_stage.copy_(pcm_host, non_blocking=True)
-        c = step(pcm_stage)
+        cs = S // E2E_CHUNKS
+        main = torch.cuda.current_stream(dev)
+        copy_stream.wait_stream(main)          # the staging buffer of the previous step is free
+        with torch.cuda.stream(copy_stream):
+            for i in range(E2E_CHUNKS):
+                pcm_stage[i * cs:(i + 1) * cs].copy_(pcm_host[i * cs:(i + 1) * cs], non_blocking=True)
+                copied[i].record(copy_stream)
+        for i in range(E2E_CHUNKS):
+            main.wait_event(copied[i])
+            sl = slice(i * cs, (i + 1) * cs)
+            first.filter(pcm_stage[sl], 0.0, out=mel[sl])
+            for m in models:
+                engines[m].posteriors(mel[sl], 2, out=post[m][sl])
+        c = counts()
         if world > 1 and c:
             c = wdist.all_reduce_counters(*c)
         for m in models:
