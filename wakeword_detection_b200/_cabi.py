@@ -331,6 +331,19 @@ class Engine:
                                                post.ctypes.data))
         return post
 
+    def _cached_const(self, kind: str, arr: np.ndarray):
+        """Device copy of a small host array (segment offsets, threshold grids), reused while its content is unchanged:
+        a sweep calls eval_counts with the same tables every step, and four pageable H2D copies per step were most of
+        the 'counts' stage."""
+        cache = self.__dict__.setdefault("_const_cache", {})
+        key = (kind, arr.dtype.str, arr.shape, hash(arr.tobytes()))
+        hit = cache.get(key)
+        if hit is None:
+            if len(cache) > 64:
+                cache.clear()
+            hit = cache[key] = self.torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+        return hit
+
     def eval_counts(self, post, seg_off: Sequence[int], thresholds, mode: str, smooth: int = 30,
                     halo_lo=None, halo_hi=None):
         """FAR/FRR numerators -> int64 tensor [n_thr] on the device."""
@@ -352,8 +365,8 @@ class Engine:
         n_total = int(seg[-1])
         if n_total > p.numel():
             raise ValueError("seg_off exceeds the posterior buffer")
-        d_seg = t.from_numpy(seg).to(self.device)
-        d_thr = t.from_numpy(thr).to(self.device)
+        d_seg = self._cached_const("seg", seg)
+        d_thr = self._cached_const("thr", thr)
         d_lo = self._dev(np.asarray(halo_lo, np.int32), t.int32) if halo_lo is not None else None
         d_hi = self._dev(np.asarray(halo_hi, np.int32), t.int32) if halo_hi is not None else None
         counts = t.zeros((thr.size,), dtype=t.int64, device=self.device)
