@@ -165,49 +165,12 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uin
       : "memory");
 }
 
-__device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-
 __device__ __forceinline__ void atomic_max_float(int* addr, float v) {
   if (v >= 0.f) atomicMax(addr, __float_as_int(v));
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(WN_EPI_THREADS) : "memory"); }
-
-// ---- cross-warp progress counters (shared memory) ------------------------------------------
-// Each warp adds 1 when it has finished a step for its tile; the warp that brings the count to a
-// multiple of 4 is the last of the tile and issues the tile's next GEMM itself.
-__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t* p, uint32_t v) {
-  uint32_t old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
-  return old;
-}
-// all lanes call; true (in every lane) for the last of the tile's four warps.  Release/acquire at CTA scope.
-__device__ __forceinline__ bool arrive_is_last(uint32_t* cnt, int lane) {
-  uint32_t old = 0;
-  __syncwarp();
-  if (lane == 0) old = atom_add_acq_rel_shared(cnt, 1u);
-  old = __shfl_sync(0xffffffffu, old, 0);
-  return (old & 3u) == 3u;
-}
-// wait until *cnt >= target (lane 0 polls)
-__device__ __forceinline__ void wait_count(const uint32_t* cnt, uint32_t target, int lane) {
-  if (lane == 0) {
-    uint32_t spins = 0;
-    while ((int32_t)(ld_acquire_shared(cnt) - target) < 0) {
-      if (++spins > (1u << 26)) __trap();
-    }
-  }
-  __syncwarp();
-}
 
 // ---- hang diagnosis (compile with -DWWB_HANG_DEBUG and pass a debug buffer): instead of trapping, the first
 // thread whose wait times out dumps its position and the shared progress counters behind the timeline
@@ -228,10 +191,8 @@ __device__ __noinline__ void wn_hang(long long* dbg, const uint32_t* cnt_u, cons
 }
 #define WN_HANG(id) wn_hang(P.dbg, nullptr, nullptr, id, tile, q, n_gate, n_rs, n_u, n_w)
 #define WN_MBAR_WAIT(bar, par, id) do { if (!mbar_try_wait(bar, par)) { uint32_t sp_ = 0; while (!mbar_try_wait(bar, par)) if (++sp_ > WN_SPIN_LIMIT) WN_HANG(id); } } while (0)
-#define WN_WAIT_COUNT(cnt, target, id) do { if (lane == 0) { uint32_t sp_ = 0; while ((int32_t)(ld_acquire_shared(cnt) - (target)) < 0) if (++sp_ > (WN_SPIN_LIMIT << 4)) WN_HANG(id); } __syncwarp(); } while (0)
 #else
 #define WN_MBAR_WAIT(bar, par, id) mbar_wait(bar, par)
-#define WN_WAIT_COUNT(cnt, target, id) wait_count(cnt, target, lane)
 #endif
 
 __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcParams P) {
