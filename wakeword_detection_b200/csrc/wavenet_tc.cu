@@ -119,6 +119,14 @@ __device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0
 __device__ __forceinline__ u64 fsub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ u64 relu2(u64 v) { float a, b; upk(v, a, b); return pk(fmaxf(a, 0.f), fmaxf(b, 0.f)); }
+// acc + ReLU(v) for a pair in two packed instructions: v + |v| = 2 max(v, 0) exactly (FADD2 takes |.| as an operand
+// modifier), and fma(., 0.5, acc) rounds once - bit-identical to acc + max(v, 0), one instruction less than
+// 2 FMNMX + FADD2, and on the FMA pipe instead of the busier ALU pipe.
+__device__ __forceinline__ u64 add_relu2(u64 acc, u64 v) {
+  float a, b;
+  upk(v, a, b);
+  return ffma2(fadd2(v, pk(fabsf(a), fabsf(b))), pk(0.5f, 0.5f), acc);
+}
 
 // split a pair into fp16 hi (mantissa truncated to 10 bits) and fp16 lo (= x - hi, exact in fp32)
 __device__ __forceinline__ void split2(u64 v, uint32_t& hi, uint32_t& lo) {
@@ -370,7 +378,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             for (int p = 0; p < 4; ++p) {
               const ulonglong2 bmv = bm[p >> 1], bav = ba[p >> 1];
               const int c = h8 * 4 + p;
-              x[c] = fadd2(relu2(pk(r[2 * p], r[2 * p + 1])), x[c]);
+              x[c] = add_relu2(x[c], pk(r[2 * p], r[2 * p + 1]));
               const u64 u = ffma2(x[c], (p & 1) ? bmv.y : bmv.x, (p & 1) ? bav.y : bav.x);
               split2(u, ur[c], ur[8 + c]);
             }
@@ -396,7 +404,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           tmem_ld8(tbase + WN_C_R + 16 + h8 * 8, s);
           tmem_ld_wait();
 #pragma unroll
-          for (int p = 0; p < 4; ++p) skip[h8 * 4 + p] = fadd2(skip[h8 * 4 + p], relu2(pk(s[2 * p], s[2 * p + 1])));
+          for (int p = 0; p < 4; ++p) skip[h8 * 4 + p] = add_relu2(skip[h8 * 4 + p], pk(s[2 * p], s[2 * p + 1]));
         }
         fence_before_sync();
         if (last) {
