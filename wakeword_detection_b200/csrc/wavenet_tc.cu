@@ -10,17 +10,20 @@
 //               in the row index, so a dilated tap is a start-address offset;
 //               tap 2 (no shift) reads A straight from TENSOR MEMORY, where the row's owner
 //               thread stored it (tcgen05.st): 15.5 clk per MMA instead of 39.4 (tools/tc_rate_probe.cu)
-//   epilogue 1  g = tanh(.)*sigmoid(.) (ex2/rcp), fp16 hi/lo -> TMEM (A operand of the next GEMM)
-//   res/skip    D[128,48] = g[128,16] * [Wres | Wskip]       (A from TMEM, accumulator shared with the gate)
-//   epilogue 2  x += ReLU(res); skip += ReLU(.); u = BN_next(x) -> hi/lo -> shared memory + TMEM
-// then the detect head (32->32 on the tensor core, A from TMEM; 32->2, max over time, softmax).
+//   epilogue 1  g = tanh(.)*sigmoid(.) (2 ex2 per channel, 1 rcp per channel pair), fp16 hi/lo -> TMEM, over the
+//               consumed gate accumulator (A operand of the next GEMM)
+//   res/skip    D[128,48] = g[128,16] * [Wres | Wskip]       (A from TMEM, own accumulator columns)
+//   epilogue 2a x += ReLU(res); u = BN_next(x) -> hi/lo -> shared memory + TMEM   (releases the next gate GEMM)
+//   epilogue 2b skip += ReLU(.)                                                   (overlaps that GEMM)
+// The input 1x1 conv (mel rows as three fp16 hi/lo k-chunks in TMEM) and the detect head (32->32 with A from
+// TMEM; then 32->2, max over time, softmax) are tensor-core GEMMs of the same kind at the group boundaries.
 // Biases are added by the tensor core too: one extra k-step whose A chunk is the constant (1, 1, 0, ...)
 // and whose B rows hold (bias_hi, bias_lo, 0, ...) - broadcast loads of per-block constants from shared
 // memory cost one wavefront per 4 bytes and were the largest shared-memory consumer (profiles/).
 // The gate weights and biases are pre-scaled by -2*log2(e) (tanh half) / -log2(e) (sigmoid half).
 // fp16 hi/lo operand split (3 MMAs per product) keeps the result at fp32 accuracy
 // (DESIGN.md §precision).  Epilogue arithmetic uses the packed fp32x2 instructions (FFMA2/FADD2).
-// Per-block weights (9.5 KB) stream through a 4-stage cp.async.bulk ring.
+// Per-block weights (12 KB incl. the bias operands) stream through a 4-stage cp.async.bulk ring.
 //
 // GEMM issue: one extra warp issues the gate GEMMs tile after tile (in order, so they run back to back and
 // stagger the tiles: the tensor pipe, the SFU and the FMA/ALU pipes then work on different tiles at the
