@@ -85,7 +85,7 @@ struct WnSmem {
   uint64_t bar_in_rdy[WN_NT], bar_in[WN_NT]; // input layer: mel rows stored to TMEM -> gate warp ; its GEMM completed
   uint64_t wfull[WN_WST];
   uint32_t tmem_base;
-  int zmax[WN_G][2];
+  int zmax[2][WN_G][2];                      // per-window max of the two logits, double-buffered by group parity
 };
 
 struct WnTcParams {
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
   for (int i = tid; i < (int)(sizeof(sm.U) / 16); i += WN_THREADS) reinterpret_cast<uint4*>(sm.U)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < (int)(sizeof(WnHead) / 16); i += WN_THREADS)
     reinterpret_cast<uint4*>(&sm.head)[i] = reinterpret_cast<const uint4*>(P.head)[i];
-  if (tid < WN_G * 2) sm.zmax[tid >> 1][tid & 1] = (int)0xff800000;   // -inf
+  if (tid < 2 * WN_G * 2) (&sm.zmax[0][0][0])[tid] = (int)0xff800000;   // -inf
   if (tid == 0) {
     for (int i = 0; i < WN_NT; ++i) {
       mbar_init(&sm.bar_u[i], 4); mbar_init(&sm.bar_g[i], 4); mbar_init(&sm.bar_gate[i], 1); mbar_init(&sm.bar_rs[i], 1);
@@ -256,6 +256,17 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     }
     const u64 ZERO2 = pk(0.f, 0.f), ONE2 = pk(1.f, 1.f);
 
+    // The mel row of the NEXT group is fetched into registers before this group's detect epilogue (x / skip are dead
+    // by then), so its global-memory latency is not on the group-boundary chain.
+    float4 mrow[10];
+    auto fetch_mel = [&](int64_t grp_next) {
+      const int64_t bn = grp_next * WN_G + w;
+      const bool vn = (grp_next < n_groups) && (w < WN_G) && (t < L) && (bn < n_win);
+      const float4* row = reinterpret_cast<const float4*>(win_row(P.wm, vn ? bn : 0, vn ? t : 0));
+#pragma unroll
+      for (int i = 0; i < 10; ++i) mrow[i] = vn ? __ldg(row + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if ((int64_t)blockIdx.x < n_groups) fetch_mel(blockIdx.x);
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++n_u) {
       const int64_t b = grp * WN_G + w;
       const bool valid = (w < WN_G) && (t < L) && (b < n_win);
@@ -265,15 +276,13 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       //  4 shared-memory wavefronts each.)  The row's 40 mel values go to TMEM as three fp16 hi/lo k-chunks (the res/skip
       //  accumulator columns are free at this point); the gate warp issues D[128,16] = mel * in_w^T (+ bias k-step).
       {
-        const float4* row = reinterpret_cast<const float4*>(win_row(P.wm, valid ? b : 0, valid ? t : 0));
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           uint32_t ar[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             if (c * 4 + j4 < 10) {
-              float4 m = __ldg(row + c * 4 + j4);
-              if (!valid) m = make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 m = mrow[c * 4 + j4];
               split2(pk(m.x, m.y), ar[2 * j4], ar[8 + 2 * j4]);
               split2(pk(m.z, m.w), ar[2 * j4 + 1], ar[8 + 2 * j4 + 1]);
             } else {
@@ -437,6 +446,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           dst[n] = make_float4(s0, s1, s2, s3);
         }
       }
+      fetch_mel(grp + gridDim.x);   // next group's mel row: in flight during the detect epilogue
       // ---- detect head epilogue: ReLU(D + b1) -> 32->2 -> max over time ----
       WN_MBAR_WAIT(&sm.bar_det[tile], n_u & 1, 8);
       fence_after_sync();
@@ -454,24 +464,25 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         }
       }
       fence_before_sync();
+      const int zp = (int)(n_u & 1);
       if (valid) {
-        atomic_max_float(&sm.zmax[w][0], z0);
-        atomic_max_float(&sm.zmax[w][1], z1);
+        atomic_max_float(&sm.zmax[zp][w][0], z0);
+        atomic_max_float(&sm.zmax[zp][w][1], z1);
       }
-      epi_bar_sync();
+      epi_bar_sync();   // the only barrier per group: zmax is double-buffered, the reset below is ordered before the
+                        // atomics of group g+2 by the barrier of group g+1
       if (tid < WN_G) {
         const int64_t bb = grp * WN_G + tid;
         if (bb < n_win) {
-          const float a0 = __int_as_float(sm.zmax[tid][0]), a1 = __int_as_float(sm.zmax[tid][1]);
+          const float a0 = __int_as_float(sm.zmax[zp][tid][0]), a1 = __int_as_float(sm.zmax[zp][tid][1]);
           const float m = fmaxf(a0, a1);
           const float e0 = expf(a0 - m), e1 = expf(a1 - m), s = e0 + e1;
           if (P.det_out) { P.det_out[bb * 2] = e0 / s; P.det_out[bb * 2 + 1] = e1 / s; }
           if (P.post) P.post[bb] = e1 / s;
         }
-        sm.zmax[tid][0] = (int)0xff800000;   // -inf for the next group
-        sm.zmax[tid][1] = (int)0xff800000;
+        sm.zmax[zp][tid][0] = (int)0xff800000;   // -inf for the group after next
+        sm.zmax[zp][tid][1] = (int)0xff800000;
       }
-      epi_bar_sync();
     }
   } else if (warp == WN_EPI_WARPS) {
     // =========================== gate-GEMM warp + weight loader ===========================
