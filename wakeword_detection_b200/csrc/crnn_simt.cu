@@ -214,9 +214,10 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
   // chunk the batch so the conv intermediate stays bounded (48.6 KB per window)
   // a multiple of 128 windows x 2 CTAs x 148 SMs (the recurrence kernel's wave)
   const int64_t chunk = 37888;
-  void *conv, *xw, *s1, *enc_ws;
+  void *conv = nullptr, *xw, *s1, *enc_ws;
   int rc;
-  if ((rc = workspace(ctx, 1, (size_t)std::min(B, chunk) * C_T * C_FEAT * 4, &conv))) return rc;
+  // the 48.6 KB/window conv intermediate exists only on the fp32 validation path (1.8 GB per chunk)
+  if (ctx->precision == WWB_PREC_F32 && (rc = workspace(ctx, 1, (size_t)std::min(B, chunk) * C_T * C_FEAT * 4, &conv))) return rc;
   if ((rc = workspace(ctx, 2, (size_t)((std::min(B, chunk) + 127) / 128 * 128) * C_T * 2 * C_G * 4, &xw))) return rc;
   if ((rc = workspace(ctx, 3, (size_t)std::min(B, chunk) * C_T * 64 * 4, &s1))) return rc;
   if ((rc = workspace(ctx, 4, (size_t)std::min(B, chunk) * 64 * 4, &enc_ws))) return rc;

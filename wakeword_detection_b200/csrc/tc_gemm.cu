@@ -44,7 +44,17 @@ tc_gemm_bias_kernel(const float* __restrict__ A, const unsigned char* __restrict
   GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_ks = K / G_KS;
-  const int64_t n_tiles = (M + 127) / 128;
+  // xw_layout: M = B*19 rows (window b, step t).  A tile is then 128 consecutive WINDOWS at ONE step t, so that a
+  // warp's stores into [b / 128][t][column][b % 128] are 512 contiguous bytes.  (With 128 consecutive (b, t) rows per
+  // tile every lane wrote its own 16 bytes 98 KB apart: 33 M scattered sector writes per launch, ~3/4 of what the L2
+  // accepts - that, not HBM, bounded the kernel.)
+  const int64_t n_win = xw_layout ? M / 19 : 0;
+  const int64_t n_tiles = xw_layout ? ((n_win + 127) / 128) * 19 : (M + 127) / 128;
+  auto row_of = [&](int64_t tile, int r) -> int64_t {     // global row of tile row r, or -1
+    if (!xw_layout) { const int64_t g = tile * 128 + r; return g < M ? g : -1; }
+    const int64_t bt = tile / 19, b = bt * 128 + r;
+    return b < n_win ? b * 19 + (tile - bt * 19) : -1;
+  };
 
   if (tid == 0) {
     for (int s = 0; s < G_STAGES; ++s) { mbar_init(&sm.full[s], G_PRODUCERS + 1); mbar_init(&sm.empty[s], 1); }
@@ -76,10 +86,10 @@ tc_gemm_bias_kernel(const float* __restrict__ A, const unsigned char* __restrict
         for (int cc = 0; cc < 2; ++cc) {
           const int r = warp * 16 + rr * 8 + r8;
           const int c = cc * 4 + cq;
-          const int64_t grow = tile * 128 + r;
+          const int64_t grow = row_of(tile, r);
           v[rr * 2 + cc][0] = make_float4(0.f, 0.f, 0.f, 0.f);
           v[rr * 2 + cc][1] = v[rr * 2 + cc][0];
-          if (grow < M) {
+          if (grow >= 0) {
             const float4* src = reinterpret_cast<const float4*>(A + grow * K + ks * G_KS + c * 8);
             v[rr * 2 + cc][0] = __ldg(src);
             v[rr * 2 + cc][1] = __ldg(src + 1);
@@ -172,14 +182,14 @@ tc_gemm_bias_kernel(const float* __restrict__ A, const unsigned char* __restrict
       const int ab = tcount & 1;
       mbar_wait(&sm.accfull[ab], (tcount >> 1) & 1);
       fence_after_sync();
-      const int64_t grow = tile * 128 + q * 32 + lane;
+      const int64_t grow = row_of(tile, q * 32 + lane);
       const uint32_t taddr = tmem + ab * 256 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < G_N; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + c0, v);
         tmem_ld_wait();
-        if (grow < M) {
+        if (grow >= 0) {
           // xw_layout: rows are (window b, t) pairs and the output goes to the coalesced layout of the
           // recurrence kernel, [b / 128][t][48 float4 columns][b % 128] (crnn_tc.cu)
           const int64_t b = grow / 19;
@@ -227,7 +237,7 @@ int tc_gemm_bias(wwb_ctx* ctx, const float* A, const unsigned char* Bpacked, con
   if (K % G_KS) return fail(ctx, WWB_ERR_ARG, "tc_gemm: K must be a multiple of %d", G_KS);
   const size_t smem = sizeof(GemmSmem) + 128;
   WWB_CUDA(ctx, cudaFuncSetAttribute(tc_gemm_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t n_tiles = (M + 127) / 128;
+  const int64_t n_tiles = xw_layout ? ((M / 19 + 127) / 128) * 19 : (M + 127) / 128;
   const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, ctx->sm_count);
   tc_gemm_bias_kernel<<<grid, G_THREADS, smem, st>>>(A, Bpacked, bias, C, M, K, nsplit, xw_layout);
   WWB_CHECK_LAUNCH(ctx);
