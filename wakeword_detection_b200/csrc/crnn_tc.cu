@@ -55,7 +55,7 @@ struct CaSmem {
   unsigned char a1[CA_CR][2 * CA_A1_PLANE];
   unsigned char w1[CA_W1_SLOTS][CA_W1_SLICE];
   unsigned char cw[2 * CA_CW_PLANE];
-  float conv_b[32];
+  unsigned char cbias_B[2 * 32 * 16];   // conv bias as the B operand of a 'ones' k-step: row n = (hi, lo, 0, ...); second chunk 0
   float b_in[192];
   uint64_t xp_full[3], xp_empty[3], cacc_full[CA_CR], cacc_empty[CA_CR], a1_full[CA_CR], a1_empty[CA_CR];
   uint64_t w1_full[CA_W1_SLOTS], w1_empty[CA_W1_SLOTS], pacc_full[2], pacc_empty[2];
@@ -95,7 +95,13 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
   for (int i = tid; i < (int)(sizeof(sm.xp) / 16); i += CA_THREADS) reinterpret_cast<uint4*>(sm.xp)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < (int)(sizeof(sm.cw) / 16); i += CA_THREADS)
     reinterpret_cast<uint4*>(sm.cw)[i] = reinterpret_cast<const uint4*>(P.cw)[i];
-  if (tid < 32) sm.conv_b[tid] = P.conv_b[tid];
+  if (tid < 64) reinterpret_cast<uint4*>(sm.cbias_B)[tid] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  if (tid < 32) {
+    __half bh, bl;
+    split_f16(P.conv_b[tid], bh, bl);
+    reinterpret_cast<uint32_t*>(sm.cbias_B + tid * 16)[0] = pack_h2(bh, bl);
+  }
   if (tid < 192) sm.b_in[tid] = P.b_in[tid];
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(&sm.xp_full[i], CA_PROD_WARPS); mbar_init(&sm.xp_empty[i], 1); }
@@ -113,7 +119,18 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
-  const uint32_t TM_CACC = 0, TM_PACC = 128;   // conv acc ring: 3 x 32 cols; projection acc: 2 x 192 cols
+  const uint32_t TM_CACC = 0, TM_ONE = 96, TM_PACC = 128;   // conv acc ring: 3 x 32 cols; constant A chunk (1, 1, 0, ...); projection acc: 2 x 192 cols
+  if (warp < 4) {   // one warp per TMEM lane quadrant writes the constant chunk before anybody can issue an MMA
+    uint32_t one[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) one[i] = 0u;
+    one[0] = 0x3c003c00u;   // (1.0h, 1.0h): the conv bias is added on the tensor core (k-step with this A chunk)
+    tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + TM_ONE, one);
+    tmem_st_wait();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
 
   if (warp < CA_EPI_WARPS) {
     // =========================== epilogue warps: one row each ===========================
@@ -122,6 +139,7 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
     const int wl = r / CA_TP, t = r - wl * CA_TP;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t tcount = 0;
+
     // Projection epilogue (+ b_in -> xw1), 16 columns at a time.  It is DEFERRED: the accumulator of
     // tile n is drained in 12 pieces during the first 12 conv steps of tile n+1 (the projection
     // accumulator is double-buffered), because its 48 scattered 16-byte stores per row would
@@ -159,13 +177,15 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         uint4 hi[4], lo[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float x[8];
+          uint32_t h[4], l[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a = (c < 2) ? v0[c * 8 + i] : v1[(c - 2) * 8 + i];
-            x[i] = fmaxf(a + sm.conv_b[c * 8 + i], 0.f);
+          for (int p = 0; p < 4; ++p) {
+            const float a0 = (c < 2) ? v0[c * 8 + 2 * p] : v1[(c - 2) * 8 + 2 * p];
+            const float a1 = (c < 2) ? v0[c * 8 + 2 * p + 1] : v1[(c - 2) * 8 + 2 * p + 1];
+            split2(pk(fmaxf(a0, 0.f), fmaxf(a1, 0.f)), h[p], l[p]);   // bias already in the accumulator
           }
-          split8v(x, hi[c], lo[c]);
+          hi[c] = make_uint4(h[0], h[1], h[2], h[3]);
+          lo[c] = make_uint4(l[0], l[1], l[2], l[3]);
         }
         mbar_wait(&sm.a1_empty[cb], cph ^ 1);
         unsigned char* a1 = sm.a1[cb] + r * 16;
@@ -252,6 +272,7 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
               mma_f16_ss(cacc, dah, dbl, idesc_c, true);
             }
           }
+          mma_f16_ts(cacc, tmem + TM_ONE, make_desc(smem_u32(sm.cbias_B), 512, 128), idesc_c, true);   // + conv bias
           mma_commit(&sm.cacc_full[cb]);
           // group f/4 was last read by conv(f) when f = 4*(f/4)
           if ((f & 3) == 0) mma_commit(&sm.xp_empty[(gbase + (f >> 2)) % 3]);
