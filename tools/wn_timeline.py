@@ -19,3 +19,5 @@ for k in range(2, 7):
 print("period per block (issuer G0), two consecutive groups:", np.diff(d[5, :, 0]))
 print("tile 0..4 gate_wake around the group boundary (blocks 22, 23 | 0, 1):", [(d[t, 22:26, 0] - t0).tolist() for t in range(5)])
 print("tile 0..4 e2a done (blocks 22, 23 | 0, 1):", [(d[t, 22:26, 3] - t0).tolist() for t in range(5)])
+print("tile 0 boundary (rel. clk): e2b(23) done, detect GEMM done, detect epilogue done, barrier+finalise done | next group: mel chunks stored, input GEMM done, first gate_wake:",
+      (d[6, 20, :4] - t0).tolist(), (d[6, 24 + 21, :2] - t0).tolist(), int(d[0, 24, 0] - t0))

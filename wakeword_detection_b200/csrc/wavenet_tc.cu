@@ -221,6 +221,23 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
 #pragma unroll
       for (int i = 0; i < 10; ++i) mrow[i] = vn ? __ldg(row + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    int64_t fin_grp = -1;
+    int fin_zp = 0;
+    auto finalise = [&]() {
+      if (fin_grp >= 0 && tid < WN_G) {
+        const int64_t bb = fin_grp * WN_G + tid;
+        if (bb < n_win) {
+          const float a0 = __int_as_float(sm.zmax[fin_zp][tid][0]), a1 = __int_as_float(sm.zmax[fin_zp][tid][1]);
+          const float m = fmaxf(a0, a1);
+          const float e0 = expf(a0 - m), e1 = expf(a1 - m), s = e0 + e1;
+          if (P.det_out) { P.det_out[bb * 2] = e0 / s; P.det_out[bb * 2 + 1] = e1 / s; }
+          if (P.post) P.post[bb] = e1 / s;
+        }
+        sm.zmax[fin_zp][tid][0] = (int)0xff800000;   // -inf for the group after next
+        sm.zmax[fin_zp][tid][1] = (int)0xff800000;
+      }
+      fin_grp = -1;
+    };
     if ((int64_t)blockIdx.x < n_groups) fetch_mel(blockIdx.x);
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++n_u) {
       const int64_t b = grp * WN_G + w;
@@ -250,10 +267,13 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.bar_in_rdy[tile]);
+        if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 0);   // mel chunks stored
+        finalise();   // previous group's posteriors, while the input GEMM runs
 #pragma unroll
         for (int n = 0; n < 16; ++n) skip[n] = ZERO2;
         WN_MBAR_WAIT(&sm.bar_in[tile], n_u & 1, 12);
         fence_after_sync();
+        if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 1);   // input GEMM done
         uint32_t ur[16];
 #pragma unroll
         for (int h8 = 0; h8 < 2; ++h8) {
@@ -401,22 +421,38 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           dst[n] = make_float4(s0, s1, s2, s3);
         }
       }
+      if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 0);   // boundary timeline: e2b(23) done
       fetch_mel(grp + gridDim.x);   // next group's mel row: in flight during the detect epilogue
       // ---- detect head epilogue: ReLU(D + b1) -> 32->2 -> max over time ----
       WN_MBAR_WAIT(&sm.bar_det[tile], n_u & 1, 8);
       fence_after_sync();
-      float z0 = sm.head.det2_b[0], z1 = sm.head.det2_b[1];
+      if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 1);   // detect GEMM done
+      // 32 -> 2 with 128-bit loads of the constants and four independent partial sums per logit (as 96 scalar loads
+      // feeding two 32-long dependent FMA chains this epilogue took ~2500 clk on the group-boundary critical path)
+      float z0, z1;
+      {
+        u64 acc0[2] = {pk(0.f, 0.f), pk(0.f, 0.f)}, acc1[2] = {pk(0.f, 0.f), pk(0.f, 0.f)};
 #pragma unroll
-      for (int h8 = 0; h8 < 4; ++h8) {
-        float d[8];
-        tmem_ld8(tbase + WN_C_R + h8 * 8, d);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float e = fmaxf(d[i] + sm.head.det1_b[h8 * 8 + i], 0.f);
-          z0 = fmaf(sm.head.det2_w[h8 * 8 + i], e, z0);
-          z1 = fmaf(sm.head.det2_w[32 + h8 * 8 + i], e, z1);
+        for (int h8 = 0; h8 < 4; ++h8) {
+          float d[8];
+          tmem_ld8(tbase + WN_C_R + h8 * 8, d);
+          const ulonglong2* b1 = reinterpret_cast<const ulonglong2*>(sm.head.det1_b + h8 * 8);
+          const ulonglong2* w0 = reinterpret_cast<const ulonglong2*>(sm.head.det2_w + h8 * 8);
+          const ulonglong2* w1 = reinterpret_cast<const ulonglong2*>(sm.head.det2_w + 32 + h8 * 8);
+          const ulonglong2 b1a = b1[0], b1b = b1[1], w0a = w0[0], w0b = w0[1], w1a = w1[0], w1b = w1[1];
+          tmem_ld_wait();
+          const u64 e0 = relu2(fadd2(pk(d[0], d[1]), b1a.x)), e1 = relu2(fadd2(pk(d[2], d[3]), b1a.y));
+          const u64 e2 = relu2(fadd2(pk(d[4], d[5]), b1b.x)), e3 = relu2(fadd2(pk(d[6], d[7]), b1b.y));
+          acc0[0] = ffma2(w0a.x, e0, acc0[0]); acc0[1] = ffma2(w0a.y, e1, acc0[1]);
+          acc0[0] = ffma2(w0b.x, e2, acc0[0]); acc0[1] = ffma2(w0b.y, e3, acc0[1]);
+          acc1[0] = ffma2(w1a.x, e0, acc1[0]); acc1[1] = ffma2(w1a.y, e1, acc1[1]);
+          acc1[0] = ffma2(w1b.x, e2, acc1[0]); acc1[1] = ffma2(w1b.y, e3, acc1[1]);
         }
+        float a, b;
+        upk(fadd2(acc0[0], acc0[1]), a, b);
+        z0 = (a + b) + sm.head.det2_b[0];
+        upk(fadd2(acc1[0], acc1[1]), a, b);
+        z1 = (a + b) + sm.head.det2_b[1];
       }
       fence_before_sync();
       const int zp = (int)(n_u & 1);
@@ -424,21 +460,14 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         atomic_max_float(&sm.zmax[zp][w][0], z0);
         atomic_max_float(&sm.zmax[zp][w][1], z1);
       }
-      epi_bar_sync();   // the only barrier per group: zmax is double-buffered, the reset below is ordered before the
-                        // atomics of group g+2 by the barrier of group g+1
-      if (tid < WN_G) {
-        const int64_t bb = grp * WN_G + tid;
-        if (bb < n_win) {
-          const float a0 = __int_as_float(sm.zmax[zp][tid][0]), a1 = __int_as_float(sm.zmax[zp][tid][1]);
-          const float m = fmaxf(a0, a1);
-          const float e0 = expf(a0 - m), e1 = expf(a1 - m), s = e0 + e1;
-          if (P.det_out) { P.det_out[bb * 2] = e0 / s; P.det_out[bb * 2 + 1] = e1 / s; }
-          if (P.post) P.post[bb] = e1 / s;
-        }
-        sm.zmax[zp][tid][0] = (int)0xff800000;   // -inf for the group after next
-        sm.zmax[zp][tid][1] = (int)0xff800000;
-      }
+      if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 2);   // detect epilogue done
+      epi_bar_sync();   // the only barrier per group: zmax is double-buffered, and its reset (in finalise, which runs
+                        // before the barrier of group g+1) is ordered before the atomics of group g+2
+      fin_grp = grp;    // softmax + stores of this group's posteriors: deferred into the next group's input-GEMM wait
+      fin_zp = zp;
+      if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 3);   // barrier done
     }
+    finalise();
   } else if (warp == WN_EPI_WARPS) {
     // =========================== gate-GEMM warp + weight loader ===========================
     // Issues the gate GEMMs tile after tile, each as soon as the tile's epilogue 2 has arrived.  Because one
