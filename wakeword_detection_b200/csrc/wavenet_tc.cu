@@ -131,10 +131,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void atomic_max_float(int* addr, float v) {
-  if (v >= 0.f) atomicMax(addr, __float_as_int(v));
-  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
-}
+// order-preserving float <-> int key (signed compare): the per-window maxima are kept as keys, so one warp-wide
+// integer max-reduction (REDUX) and one atomicMax per warp replace 32 serialised shared-memory atomics
+__device__ __forceinline__ int f2key(float v) { const int i = __float_as_int(v); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float key2f(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+constexpr int WN_KEY_NEG_INF = (int)0x807fffff;   // f2key(-inf)
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(WN_EPI_THREADS) : "memory"); }
 
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
   for (int i = tid; i < (int)(sizeof(sm.U) / 16); i += WN_THREADS) reinterpret_cast<uint4*>(sm.U)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < (int)(sizeof(WnHead) / 16); i += WN_THREADS)
     reinterpret_cast<uint4*>(&sm.head)[i] = reinterpret_cast<const uint4*>(P.head)[i];
-  if (tid < 2 * WN_G * 2) (&sm.zmax[0][0][0])[tid] = (int)0xff800000;   // -inf
+  if (tid < 2 * WN_G * 2) (&sm.zmax[0][0][0])[tid] = WN_KEY_NEG_INF;
   if (tid == 0) {
     for (int i = 0; i < WN_NT; ++i) {
       mbar_init(&sm.bar_u[i], 4); mbar_init(&sm.bar_g[i], 4); mbar_init(&sm.bar_gate[i], 1); mbar_init(&sm.bar_rs[i], 1);
@@ -227,16 +228,38 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       if (fin_grp >= 0 && tid < WN_G) {
         const int64_t bb = fin_grp * WN_G + tid;
         if (bb < n_win) {
-          const float a0 = __int_as_float(sm.zmax[fin_zp][tid][0]), a1 = __int_as_float(sm.zmax[fin_zp][tid][1]);
+          const float a0 = key2f(sm.zmax[fin_zp][tid][0]), a1 = key2f(sm.zmax[fin_zp][tid][1]);
           const float m = fmaxf(a0, a1);
           const float e0 = expf(a0 - m), e1 = expf(a1 - m), s = e0 + e1;
           if (P.det_out) { P.det_out[bb * 2] = e0 / s; P.det_out[bb * 2 + 1] = e1 / s; }
           if (P.post) P.post[bb] = e1 / s;
         }
-        sm.zmax[fin_zp][tid][0] = (int)0xff800000;   // -inf for the group after next
-        sm.zmax[fin_zp][tid][1] = (int)0xff800000;
+        sm.zmax[fin_zp][tid][0] = WN_KEY_NEG_INF;   // for the group after next
+        sm.zmax[fin_zp][tid][1] = WN_KEY_NEG_INF;
       }
       fin_grp = -1;
+    };
+    // the row's 40 mel values -> three fp16 hi/lo k-chunks in the (free) res/skip accumulator columns -> gate warp
+    auto store_mel = [&]() {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint32_t ar[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          if (c * 4 + j4 < 10) {
+            const float4 m = mrow[c * 4 + j4];
+            split2(pk(m.x, m.y), ar[2 * j4], ar[8 + 2 * j4]);
+            split2(pk(m.z, m.w), ar[2 * j4 + 1], ar[8 + 2 * j4 + 1]);
+          } else {
+            ar[2 * j4] = ar[2 * j4 + 1] = ar[8 + 2 * j4] = ar[8 + 2 * j4 + 1] = 0u;
+          }
+        }
+        tmem_st16(tbase + WN_C_R + 16 * c, ar);
+      }
+      tmem_st_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.bar_in_rdy[tile]);
     };
     if ((int64_t)blockIdx.x < n_groups) fetch_mel(blockIdx.x);
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++n_u) {
@@ -248,25 +271,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       //  4 shared-memory wavefronts each.)  The row's 40 mel values go to TMEM as three fp16 hi/lo k-chunks (the res/skip
       //  accumulator columns are free at this point); the gate warp issues D[128,16] = mel * in_w^T (+ bias k-step).
       {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          uint32_t ar[16];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            if (c * 4 + j4 < 10) {
-              const float4 m = mrow[c * 4 + j4];
-              split2(pk(m.x, m.y), ar[2 * j4], ar[8 + 2 * j4]);
-              split2(pk(m.z, m.w), ar[2 * j4 + 1], ar[8 + 2 * j4 + 1]);
-            } else {
-              ar[2 * j4] = ar[2 * j4 + 1] = ar[8 + 2 * j4] = ar[8 + 2 * j4 + 1] = 0u;
-            }
-          }
-          tmem_st16(tbase + WN_C_R + 16 * c, ar);
-        }
-        tmem_st_wait();
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.bar_in_rdy[tile]);
+        store_mel();
         if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 0);   // mel chunks stored
         finalise();   // previous group's posteriors, while the input GEMM runs
 #pragma unroll
@@ -456,9 +461,22 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       }
       fence_before_sync();
       const int zp = (int)(n_u & 1);
-      if (valid) {
-        atomic_max_float(&sm.zmax[zp][w][0], z0);
-        atomic_max_float(&sm.zmax[zp][w][1], z1);
+      {
+        // a warp's 32 rows touch at most two windows (slot = 198 rows): one reduction + one atomic per window
+        const int w_first = __shfl_sync(0xffffffffu, w, 0);
+#pragma unroll
+        for (int dw = 0; dw < 2; ++dw) {
+          const bool mine = valid && (w == w_first + dw);
+          const unsigned m = __ballot_sync(0xffffffffu, mine);
+          if (m) {
+            const int k0 = __reduce_max_sync(0xffffffffu, mine ? f2key(z0) : WN_KEY_NEG_INF);
+            const int k1 = __reduce_max_sync(0xffffffffu, mine ? f2key(z1) : WN_KEY_NEG_INF);
+            if (lane == 0) {
+              atomicMax(&sm.zmax[zp][w_first + dw][0], k0);
+              atomicMax(&sm.zmax[zp][w_first + dw][1], k1);
+            }
+          }
+        }
       }
       if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 2);   // detect epilogue done
       epi_bar_sync();   // the only barrier per group: zmax is double-buffered, and its reset (in finalise, which runs
