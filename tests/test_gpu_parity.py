@@ -485,3 +485,18 @@ def test_get_posterior_and_sweep_dropin(wname, name, golden):
     np.testing.assert_array_equal(thr, golden["sweep_%s_thr" % name])
     np.testing.assert_array_equal(FRR, golden["sweep_%s_frr" % name])
     np.testing.assert_array_equal(FAR, golden["sweep_%s_far" % name])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wname", ["CRNN", "Wavenet"])
+def test_encoders_are_deterministic(wname):
+    """The tensor-core kernels hand tiles between warps through mbarriers / TMEM / shared memory; a missed
+    dependency shows up as run-to-run differences.  Same input -> bit-identical posteriors, ragged sizes included."""
+    import torch
+    eng = get_engine(wname)
+    for S, n in ((37, 52800), (3, 40000), (1, 32000)):
+        pcm = synth.device_pcm(S, n, seed=100 + S, device=eng.device)
+        mel = eng.filter(pcm)
+        ref = eng.posteriors(mel, 2).clone()
+        for _ in range(6):
+            assert torch.equal(eng.posteriors(mel, 2), ref)
