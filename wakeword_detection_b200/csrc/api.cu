@@ -215,10 +215,12 @@ static int build_wavenet(wwb_ctx* ctx, const wwb_weights* w) {
   {
     std::vector<unsigned char> blocks = wavenet_pack_blocks(gw.data(), gb.data(), rw.data(), rb.data(), w->bn_mul,
                                                             w->bn_add, N.dilation);
+    if (blocks.empty()) return fail(ctx, WWB_ERR_ARG, "WaveNet: a BatchNorm scale of 0 cannot be folded into the tensor-core path (use precision f32)");
     if ((rc = upload(ctx, blocks, &N.tc_blocks))) return rc;
     std::vector<float> in_w_kc = transposed(w->in_w, 16, 40);
     std::vector<unsigned char> head = wavenet_pack_head(in_w_kc.data(), w->in_b, w->bn_mul, w->bn_add, w->det1_w,
                                                         w->det1_b, w->det2_w, w->det2_b);
+    if (head.empty()) return fail(ctx, WWB_ERR_ARG, "WaveNet: a BatchNorm scale of 0 cannot be folded into the tensor-core path (use precision f32)");
     if ((rc = upload(ctx, head, &N.tc_head))) return rc;
   }
   if ((rc = upload(ctx, gw, &N.gate_w))) return rc;

@@ -21,6 +21,11 @@
 // and whose B rows hold (bias_hi, bias_lo, 0, ...) - broadcast loads of per-block constants from shared
 // memory cost one wavefront per 4 bytes and were the largest shared-memory consumer (profiles/).
 // The gate weights and biases are pre-scaled by -2*log2(e) (tanh half) / -log2(e) (sigmoid half).
+// The per-block BatchNorm affine u = bn_mul * x + bn_add is FOLDED into the gate GEMM (weights * bn_mul, bias +
+// W * bn_add), so the A operand is the residual stream x itself and the epilogue neither loads the 32 constants
+// (8 broadcast LDS.128 = 32 shared-memory wavefronts per warp and block, 17 % of the shared-memory pipe) nor
+// applies them.  The causal zero padding is of u, not x: the 16 padding rows in front of every window therefore
+// hold x_pad = -bn_add / bn_mul (so that u_pad = 0), rewritten for each block by the threads that own those rows.
 // fp16 hi/lo operand split (3 MMAs per product) keeps the result at fp32 accuracy
 // (DESIGN.md §precision).  Epilogue arithmetic uses the packed fp32x2 instructions (FFMA2/FADD2).
 // Per-block weights (12 KB incl. the bias operands) stream through a 4-stage cp.async.bulk ring.
@@ -52,7 +57,7 @@ constexpr int WN_EPI_WARPS = WN_NT * 4;       // 20
 constexpr int WN_EPI_THREADS = WN_EPI_WARPS * 32;
 constexpr int WN_THREADS = (WN_EPI_WARPS + 2) * 32;   // + the gate-GEMM / loader warp + the res/skip-GEMM warp = 704
 constexpr int WN_GATE_B = 6144, WN_RS_B = 3072;   // gate / res+skip B operands (hi and lo planes)
-constexpr int WN_F32_B = 512;                     // fp32 constants: [80..95] next block's BN scale, [96..111] BN shift
+constexpr int WN_F32_B = 512;                     // misc: bytes [320, 384) = the NEXT block's padding rows (hi0, hi1, lo0, lo1)
 constexpr int WN_GBIAS_B = 1024, WN_RBIAS_B = 1536;   // bias B operands for the 'ones' GEMM (k0 = hi, k1 = lo)
 constexpr int WN_OFF_F32 = WN_GATE_B + WN_RS_B, WN_OFF_GBIAS = WN_OFF_F32 + WN_F32_B, WN_OFF_RBIAS = WN_OFF_GBIAS + WN_GBIAS_B;
 constexpr int WN_WBLK = WN_OFF_RBIAS + WN_RBIAS_B;    // 12288 bytes of one block's weight blob
@@ -65,7 +70,8 @@ constexpr int WN_C_ONE = WN_NT * WN_TMEM_TILE;   // 480..487: constant A chunk (
 
 // resident head blob (floats unless noted)
 struct WnHead {
-  float bn0_mul[16], bn0_add[16];
+  unsigned char pad0[64];   // block 0's padding rows (see the BN note in the header): hi chunk 0, hi chunk 1, lo chunk 0, lo chunk 1
+  unsigned char rsv_[64];
   float det1_b[32];
   float det2_w[2 * 32];
   float det2_b[2];
@@ -202,6 +208,18 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     const uint32_t tbase = tacc + ((uint32_t)(q * 32) << 16);         // ... seen from this warp's lane quadrant
     uint32_t n_gate = 0, n_rs = 0, n_w = 0, n_u = 0;  // completed phases of bar_gate / bar_rs ; global block index ; groups done
     unsigned char* const Urow = sm.U + (16 + o) * 16;
+    // padding rows: the 16 rows after each window (they precede the next one; owned by otherwise idle threads) and,
+    // for window 0, U rows 0..15, which the threads of rows 0..15 write in addition to their own row (they belong to
+    // tile 0, whose gate GEMM is the reader, so the tile's arrival barrier orders the write)
+    const bool pad_row = (w < WN_G && t >= 182) || (o < 16);
+    unsigned char* const Upad = (o < 16) ? sm.U + o * 16 : Urow;
+    auto store_pad = [&](const unsigned char* chunk) {   // chunk: 64 bytes (hi0, hi1, lo0, lo1)
+      const uint4* c4 = reinterpret_cast<const uint4*>(chunk);
+      *reinterpret_cast<uint4*>(Upad) = c4[0];
+      *reinterpret_cast<uint4*>(Upad + WN_PU) = c4[1];
+      *reinterpret_cast<uint4*>(Upad + 2 * WN_PU) = c4[2];
+      *reinterpret_cast<uint4*>(Upad + 3 * WN_PU) = c4[3];
+    };
     {
       uint32_t one[16];
 #pragma unroll
@@ -289,9 +307,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           for (int p = 0; p < 4; ++p) {
             const int c = h8 * 4 + p;
             x[c] = relu2(pk(r[2 * p], r[2 * p + 1]));
-            const u64 u = ffma2(x[c], *reinterpret_cast<const u64*>(sm.head.bn0_mul + 2 * c),
-                                *reinterpret_cast<const u64*>(sm.head.bn0_add + 2 * c));
-            split2(u, ur[c], ur[8 + c]);
+            split2(x[c], ur[c], ur[8 + c]);
           }
         }
         if (valid) {
@@ -300,6 +316,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           *reinterpret_cast<uint4*>(Urow + 2 * WN_PU) = make_uint4(ur[8], ur[9], ur[10], ur[11]);
           *reinterpret_cast<uint4*>(Urow + 3 * WN_PU) = make_uint4(ur[12], ur[13], ur[14], ur[15]);
         }
+        if (pad_row) store_pad(sm.head.pad0);
         tmem_st16(tbase + WN_C_U, ur);
         tmem_st_wait();
         fence_before_sync();
@@ -364,15 +381,11 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             float r[8];
             tmem_ld8(tbase + WN_C_R + h8 * 8, r);
             tmem_ld_wait();
-            const ulonglong2* bm = reinterpret_cast<const ulonglong2*>(wf + 80 + h8 * 8);
-            const ulonglong2* ba = reinterpret_cast<const ulonglong2*>(wf + 96 + h8 * 8);
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
-              const ulonglong2 bmv = bm[p >> 1], bav = ba[p >> 1];
               const int c = h8 * 4 + p;
               x[c] = add_relu2(x[c], pk(r[2 * p], r[2 * p + 1]));
-              const u64 u = ffma2(x[c], (p & 1) ? bmv.y : bmv.x, (p & 1) ? bav.y : bav.x);
-              split2(u, ur[c], ur[8 + c]);
+              split2(x[c], ur[c], ur[8 + c]);   // the next block's BN is folded into its gate weights
             }
           }
           if (valid) {
@@ -381,6 +394,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             *reinterpret_cast<uint4*>(Urow + 2 * WN_PU) = make_uint4(ur[8], ur[9], ur[10], ur[11]);
             *reinterpret_cast<uint4*>(Urow + 3 * WN_PU) = make_uint4(ur[12], ur[13], ur[14], ur[15]);
           }
+          if (pad_row) store_pad(reinterpret_cast<const unsigned char*>(wf) + 320);
           tmem_st16(tbase + WN_C_U, ur);
           tmem_st_wait();
           fence_before_sync();
@@ -663,6 +677,17 @@ static void put_split(std::vector<unsigned char>& buf, size_t hi_off, size_t lo_
 
 // gate_w [24][48][32] (k = tap*16+ch ; n), rs_w [24][16][48], biases, bn, dilation (fp32 device-layout copies
 // made by api.cu on the host before upload)
+// padding rows for a block whose BatchNorm is (mul, add): x_pad = -add / mul (=> u_pad = 0), as the 64-byte
+// (hi chunk 0, hi chunk 1, lo chunk 0, lo chunk 1) image of one U row.  false if a scale is 0 (cannot be folded).
+static bool put_pad_rows(std::vector<unsigned char>& out, size_t off, const float* mul, const float* add) {
+  for (int c = 0; c < 16; ++c) {
+    if (mul[c] == 0.f) return false;
+    const size_t o = off + (size_t)(c / 8) * 16 + (c % 8) * 2;
+    put_split(out, o, o + 32, (float)(-(double)add[c] / (double)mul[c]), true);
+  }
+  return true;
+}
+
 std::vector<unsigned char> wavenet_pack_blocks(const float* gate_w, const float* gate_b, const float* rs_w,
                                                const float* rs_b, const float* bn_mul, const float* bn_add,
                                                const int* dilation) {
@@ -673,7 +698,7 @@ std::vector<unsigned char> wavenet_pack_blocks(const float* gate_w, const float*
       for (int n = 0; n < 32; ++n) {
         const int c = k / 8, e = k % 8;
         const size_t off = base + ((size_t)c * 32 + n) * 16 + e * 2;
-        put_split(out, off, off + 3072, (float)((double)gate_w[((size_t)b * 48 + k) * 32 + n] * gate_scale(n)), true);
+        put_split(out, off, off + 3072, (float)((double)gate_w[((size_t)b * 48 + k) * 32 + n] * (double)bn_mul[b * 16 + k % 16] * gate_scale(n)), true);
       }
     for (int k = 0; k < 16; ++k)
       for (int n = 0; n < 48; ++n) {
@@ -682,14 +707,15 @@ std::vector<unsigned char> wavenet_pack_blocks(const float* gate_w, const float*
         put_split(out, off, off + 1536, rs_w[((size_t)b * 16 + k) * 48 + n], true);
       }
     float f[113] = {0};
-    if (b < 23)
-      for (int c = 0; c < 16; ++c) { f[80 + c] = bn_mul[(b + 1) * 16 + c]; f[96 + c] = bn_add[(b + 1) * 16 + c]; }
     f[112] = (float)dilation[b];
     memcpy(&out[base + WN_OFF_F32], f, sizeof(f));
+    if (b < 23 && !put_pad_rows(out, base + WN_OFF_F32 + 320, bn_mul + (b + 1) * 16, bn_add + (b + 1) * 16)) return {};
     // bias operands of the 'ones' GEMM: row n = (hi, lo, 0, ...); the second k-chunk stays zero
     for (int n = 0; n < 32; ++n) {
       const size_t off = base + WN_OFF_GBIAS + (size_t)n * 16;
-      put_split(out, off, off + 2, (float)((double)gate_b[b * 32 + n] * gate_scale(n)), true);
+      double bsum = gate_b[b * 32 + n];   // + W * bn_add (the folded BatchNorm shift)
+      for (int k = 0; k < 48; ++k) bsum += (double)gate_w[((size_t)b * 48 + k) * 32 + n] * (double)bn_add[b * 16 + k % 16];
+      put_split(out, off, off + 2, (float)(bsum * gate_scale(n)), true);
     }
     for (int n = 0; n < 48; ++n) {
       const size_t off = base + WN_OFF_RBIAS + (size_t)n * 16;
@@ -704,8 +730,8 @@ std::vector<unsigned char> wavenet_pack_head(const float* in_w_kc, const float* 
                                              const float* det2_w, const float* det2_b) {
   std::vector<unsigned char> out(sizeof(WnHead), 0);
   WnHead* h = reinterpret_cast<WnHead*>(out.data());
-  memcpy(h->bn0_mul, bn_mul0, sizeof(h->bn0_mul));
-  memcpy(h->bn0_add, bn_add0, sizeof(h->bn0_add));
+  if (!put_pad_rows(out, offsetof(WnHead, pad0), bn_mul0, bn_add0)) return {};
+  h = reinterpret_cast<WnHead*>(out.data());
   memcpy(h->det1_b, det1_b, sizeof(h->det1_b));
   memcpy(h->det2_w, det2_w, sizeof(h->det2_w));
   memcpy(h->det2_b, det2_b, sizeof(h->det2_b));
