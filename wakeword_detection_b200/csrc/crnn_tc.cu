@@ -56,7 +56,7 @@ struct CaSmem {
   unsigned char w1[CA_W1_SLOTS][CA_W1_SLICE];
   unsigned char cw[2 * CA_CW_PLANE];
   unsigned char cbias_B[2 * 32 * 16];   // conv bias as the B operand of a 'ones' k-step: row n = (hi, lo, 0, ...); second chunk 0
-  float b_in[192];
+  unsigned char pbias_B[2 * 192 * 16];  // GRU-1 input bias as the B operand of a 'ones' k-step (row n = (hi, lo, 0, ...))
   uint64_t xp_full[3], xp_empty[3], cacc_full[CA_CR], cacc_empty[CA_CR], a1_full[CA_CR], a1_empty[CA_CR];
   uint64_t w1_full[CA_W1_SLOTS], w1_empty[CA_W1_SLOTS], pacc_full[2], pacc_empty[2];
   uint32_t tmem_base;
@@ -96,13 +96,18 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
   for (int i = tid; i < (int)(sizeof(sm.cw) / 16); i += CA_THREADS)
     reinterpret_cast<uint4*>(sm.cw)[i] = reinterpret_cast<const uint4*>(P.cw)[i];
   if (tid < 64) reinterpret_cast<uint4*>(sm.cbias_B)[tid] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < (int)(sizeof(sm.pbias_B) / 16); i += CA_THREADS) reinterpret_cast<uint4*>(sm.pbias_B)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   if (tid < 32) {
     __half bh, bl;
     split_f16(P.conv_b[tid], bh, bl);
     reinterpret_cast<uint32_t*>(sm.cbias_B + tid * 16)[0] = pack_h2(bh, bl);
   }
-  if (tid < 192) sm.b_in[tid] = P.b_in[tid];
+  if (tid < 192) {
+    __half bh, bl;
+    split_f16(P.b_in[tid], bh, bl);
+    reinterpret_cast<uint32_t*>(sm.pbias_B + tid * 16)[0] = pack_h2(bh, bl);
+  }
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(&sm.xp_full[i], CA_PROD_WARPS); mbar_init(&sm.xp_empty[i], 1); }
     for (int i = 0; i < CA_CR; ++i) {
@@ -154,8 +159,7 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         float4* dst = reinterpret_cast<float4*>(P.xw1) + (((pb_b >> 7) * CA_T + t) * 48 + c0 / 4) * 128 + (pb_b & 127);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          dst[i * 128] = make_float4(v[4 * i] + sm.b_in[c0 + 4 * i], v[4 * i + 1] + sm.b_in[c0 + 4 * i + 1],
-                                     v[4 * i + 2] + sm.b_in[c0 + 4 * i + 2], v[4 * i + 3] + sm.b_in[c0 + 4 * i + 3]);
+          dst[i * 128] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);   // b_in was added by the tensor core
       }
     };
     int64_t prev_b = 0;
@@ -318,7 +322,10 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
           }
           mma_commit(&sm.a1_empty[cb]);
           mma_commit(&sm.w1_empty[sl]);
-          if (f == CA_F - 1) mma_commit(&sm.pacc_full[pb]);
+          if (f == CA_F - 1) {
+            mma_f16_ts(pacc, tmem + TM_ONE, make_desc(smem_u32(sm.pbias_B), 192 * 16, 128), idesc_p, true);   // + b_in
+            mma_commit(&sm.pacc_full[pb]);
+          }
         }
         __syncwarp();
         CA_DBG(f, 7);
