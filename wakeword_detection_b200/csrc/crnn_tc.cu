@@ -52,7 +52,6 @@ constexpr int CA_THREADS = (CA_EPI_WARPS + CA_ROLE_WARPS + 2 * CA_PROD_WARPS) * 
 
 struct CaSmem {
   unsigned char xp[2 * CA_XP_PLANE];
-  unsigned char a1[CA_CR][2 * CA_A1_PLANE];
   unsigned char w1[CA_W1_SLOTS][CA_W1_SLICE];
   unsigned char cw[2 * CA_CW_PLANE];
   unsigned char cbias_B[2 * 32 * 16];   // conv bias as the B operand of a 'ones' k-step: row n = (hi, lo, 0, ...); second chunk 0
@@ -191,14 +190,19 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
           hi[c] = make_uint4(h[0], h[1], h[2], h[3]);
           lo[c] = make_uint4(l[0], l[1], l[2], l[3]);
         }
-        mbar_wait(&sm.a1_empty[cb], cph ^ 1);
-        unsigned char* a1 = sm.a1[cb] + r * 16;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          *reinterpret_cast<uint4*>(a1 + c * 2048) = hi[c];
-          *reinterpret_cast<uint4*>(a1 + CA_A1_PLANE + c * 2048) = lo[c];
+        // the fp16 hi/lo operand of the projection GEMM goes back into the conv accumulator's own 32 TMEM columns
+        // (hi: 16 columns = two k-steps, lo: 16 columns): the projection reads A from tensor memory (96 instead of
+        // 105 clk per MMA, and no shared-memory round trip of the 128 x 32 slice)
+        {
+          const uint32_t hr[16] = {hi[0].x, hi[0].y, hi[0].z, hi[0].w, hi[1].x, hi[1].y, hi[1].z, hi[1].w,
+                                   hi[2].x, hi[2].y, hi[2].z, hi[2].w, hi[3].x, hi[3].y, hi[3].z, hi[3].w};
+          const uint32_t lr[16] = {lo[0].x, lo[0].y, lo[0].z, lo[0].w, lo[1].x, lo[1].y, lo[1].z, lo[1].w,
+                                   lo[2].x, lo[2].y, lo[2].z, lo[2].w, lo[3].x, lo[3].y, lo[3].z, lo[3].w};
+          tmem_st16(tlane + TM_CACC + cb * 32, hr);
+          tmem_st16(tlane + TM_CACC + cb * 32 + 16, lr);
+          tmem_st_wait();
         }
-        fence_async_smem();
+        fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.a1_full[cb]);
         // one piece of the previous tile's projection accumulator
@@ -244,8 +248,9 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
       for (int f = 0; f < CA_F; ++f) {
         const uint32_t ci = tcount * CA_F + f;
         const int cb = ci % CA_CR;
-        // conv accumulator ci % 3 was last used by slice ci-3: its epilogue has read it once a1_full(ci-3) completed
-        if (ci >= (uint32_t)CA_CR) mbar_wait(&sm.a1_full[cb], (((ci - CA_CR) / CA_CR) & 1));
+        // conv accumulator ci % 3 was last used by slice ci-3 and then held that slice's projection operand:
+        // free once the projection GEMM of ci-3 has completed (a1_empty)
+        if (ci >= (uint32_t)CA_CR) mbar_wait(&sm.a1_empty[cb], (((ci - CA_CR) / CA_CR) & 1));
         const int g_hi = (2 * f + 12) >> 3;
         CA_DBG(f, 0);
         for (; groups_ready <= g_hi; ++groups_ready) {
@@ -308,16 +313,15 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         CA_DBG(f, 6);
         fence_after_sync();
         if (elect_one()) {
-          const uint64_t da = make_desc(smem_u32(sm.a1[cb]), 2048, 128);
+          const uint32_t ta = tmem + TM_CACC + cb * 32;   // hi k-steps at +0 / +8, lo at +16 / +24
           const uint64_t db = make_desc(smem_u32(sm.w1[sl]), 3072, 128);
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
-            const uint64_t dah = da + (uint64_t)(kk * (4096 >> 4)), dal = dah + (uint64_t)(CA_A1_PLANE >> 4);
             const uint64_t dbh = db + (uint64_t)(kk * (6144 >> 4)), dbl = dbh + (uint64_t)((CA_W1_SLICE / 2) >> 4);
-            mma_f16_ss(pacc, dah, dbh, idesc_p, (f | kk) != 0);
+            mma_f16_ts(pacc, ta + kk * 8, dbh, idesc_p, (f | kk) != 0);
             if (nsplit == 3) {
-              mma_f16_ss(pacc, dal, dbh, idesc_p, true);
-              mma_f16_ss(pacc, dah, dbl, idesc_p, true);
+              mma_f16_ts(pacc, ta + 16 + kk * 8, dbh, idesc_p, true);
+              mma_f16_ts(pacc, ta + kk * 8, dbl, idesc_p, true);
             }
           }
           mma_commit(&sm.a1_empty[cb]);
