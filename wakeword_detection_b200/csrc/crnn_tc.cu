@@ -43,7 +43,7 @@ constexpr int CA_XP_PLANE = CA_RING_ROWS * CA_PITCH;
 constexpr int CA_GROUPS = 7;                      // 8-row groups per tile (padded rows p = freq + 8, 0..55)
 constexpr int CA_A1_PLANE = 4 * 128 * 16;         // one k-slice (32 values) of 128 rows
 constexpr int CA_W1_SLICE = 2 * 4 * 192 * 16;     // hi + lo planes of one k-slice of W1
-constexpr int CA_W1_SLOTS = 2;
+constexpr int CA_W1_SLOTS = 3;
 constexpr int CA_CR = 3;                          // conv accumulator / A1 slice ring depth
 constexpr int CA_CW_PLANE = 16 * 32 * 16;         // conv weights: 16 k-chunks x 32 channels
 constexpr int CA_EPI_WARPS = 4, CA_PROD_WARPS = 4;                  // producer warps per set; two sets alternate groups
