@@ -485,11 +485,17 @@ constexpr int GR_H_BYTES = 2 * 4 * 128 * 16;     // hi + lo planes, K = 32
 constexpr int GR_U_BYTES = 2 * 4 * 96 * 16;
 constexpr int GR_THREADS = 9 * 32;
 
+constexpr int GR_X_BYTES = 24 * 128 * 16;          // one direction's xw of one step: 24 float4 columns x 128 windows (contiguous in HBM)
+constexpr int GR_XST = 2;                          // xw stages PER DIRECTION (a stage never changes its consumer warps)
+
+// h (the A operand of the recurrent GEMM) lives in TENSOR MEMORY, fp16 hi (16 columns) + lo (16 columns) per
+// direction; that frees the shared memory for a TMA-filled ring of xw slabs (2 steps x 2 directions x 48 KB).
 struct GrSmem {
-  unsigned char h[2][GR_H_BYTES];
+  unsigned char x[2][GR_XST][GR_X_BYTES];          // [direction][stage]
   unsigned char u[2][GR_U_BYTES];
   float bh[2][32];
   uint64_t acc_full[2], h_ready[2];
+  uint64_t x_full[2][GR_XST], x_empty[2][GR_XST];
   uint32_t tmem_base;
 };
 
@@ -527,7 +533,7 @@ __device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__global__ void __launch_bounds__(GR_THREADS, 2) gru_rec_tc_kernel(const GrParams P) {
+__global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GrSmem& sm = *reinterpret_cast<GrSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -539,7 +545,10 @@ __global__ void __launch_bounds__(GR_THREADS, 2) gru_rec_tc_kernel(const GrParam
     reinterpret_cast<uint4*>(&sm.u[0][0])[i] = reinterpret_cast<const uint4*>(P.u)[i];
   if (tid < 64) (&sm.bh[0][0])[tid] = P.bh[tid];
   if (tid == 0) {
-    for (int d = 0; d < 2; ++d) { mbar_init(&sm.acc_full[d], 1); mbar_init(&sm.h_ready[d], 4); }
+    for (int d = 0; d < 2; ++d) {
+      mbar_init(&sm.acc_full[d], 1); mbar_init(&sm.h_ready[d], 4);
+      for (int i = 0; i < GR_XST; ++i) { mbar_init(&sm.x_full[d][i], 1); mbar_init(&sm.x_empty[d][i], 4); }
+    }
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc(&sm.tmem_base, 256);
@@ -553,22 +562,23 @@ __global__ void __launch_bounds__(GR_THREADS, 2) gru_rec_tc_kernel(const GrParam
     const int d = warp >> 2, q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + d * 96;
-    unsigned char* hrow = sm.h[d] + r * 16;
+    const uint32_t th = tmem + ((uint32_t)(q * 32) << 16) + 192 + d * 32;   // this row's h: hi 16 columns, lo 16 columns
     const float* bh = sm.bh[d];
-    uint32_t n_acc = 0;
+    uint32_t n_acc = 0, n_x = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t b = tile * 128 + r;
       const bool valid = b < n_win;
       float h[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) h[i] = 0.f;
-      for (int s = 0; s < GR_T; ++s) {
+      for (int s = 0; s < GR_T; ++s, ++n_x) {
         const int t = d ? GR_T - 1 - s : s;
-        const float4* xp = reinterpret_cast<const float4*>(P.xw) + ((tile * GR_T + t) * 48 + d * 24) * 128 + r;
-        float4 xn[6];   // z, r, h parts of the next 8-unit chunk
-        xn[0] = __ldg(xp + 0 * 128); xn[1] = __ldg(xp + 1 * 128);
-        xn[2] = __ldg(xp + 8 * 128); xn[3] = __ldg(xp + 9 * 128);
-        xn[4] = __ldg(xp + 16 * 128); xn[5] = __ldg(xp + 17 * 128);
+        // this direction's xw slab of the step was fetched by the TMA engine one step ahead (per-thread loads could
+        // prefetch only one 400-clock chunk ahead of ~1500 clocks of DRAM latency)
+        const int xs = n_x % GR_XST;
+        mbar_wait(&sm.x_full[d][xs], (n_x / GR_XST) & 1);
+        const float4* xp = reinterpret_cast<const float4*>(sm.x[d][xs]) + r;
+        float x_last = 0.f;
         if (s > 0) {
           mbar_wait(&sm.acc_full[d], n_acc & 1);
           ++n_acc;
@@ -577,13 +587,10 @@ __global__ void __launch_bounds__(GR_THREADS, 2) gru_rec_tc_kernel(const GrParam
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float4 xc[6];
-#pragma unroll
-          for (int i = 0; i < 6; ++i) xc[i] = xn[i];
-          if (u < 3) {
-            xn[0] = __ldg(xp + (2 * u + 2) * 128); xn[1] = __ldg(xp + (2 * u + 3) * 128);
-            xn[2] = __ldg(xp + (2 * u + 10) * 128); xn[3] = __ldg(xp + (2 * u + 11) * 128);
-            xn[4] = __ldg(xp + (2 * u + 18) * 128); xn[5] = __ldg(xp + (2 * u + 19) * 128);
-          }
+          xc[0] = xp[(2 * u) * 128]; xc[1] = xp[(2 * u + 1) * 128];
+          xc[2] = xp[(2 * u + 8) * 128]; xc[3] = xp[(2 * u + 9) * 128];
+          xc[4] = xp[(2 * u + 16) * 128]; xc[5] = xp[(2 * u + 17) * 128];
+          if (u == 3) x_last = xc[5].w;
           float hz[8], hr[8], hh[8];
           if (s > 0) {
             tmem_ld8f(tbase + u * 8, hz);
@@ -605,19 +612,23 @@ __global__ void __launch_bounds__(GR_THREADS, 2) gru_rec_tc_kernel(const GrParam
             h[u * 8 + i] = fmaf(z, h[u * 8 + i] - c, c);
           }
         }
+        // hand the stage back once every lane's loads from it have completed (the arrive depends on the last loaded
+        // value of all lanes through a warp reduction)
+        {
+          uint32_t tok;
+          asm volatile("mov.b32 %0, %1;" : "=r"(tok) : "f"(x_last));
+          tok = __reduce_or_sync(0xffffffffu, tok);
+          if (lane == 0) mbar_arrive_after(&sm.x_empty[d][xs], tok);
+        }
         if (s < GR_T - 1) {
           fence_before_sync();
+          uint32_t hr16[16], lr16[16];
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            float x[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = h[c4 * 8 + i];
-            uint4 hi, lo;
-            split8v(x, hi, lo);
-            *reinterpret_cast<uint4*>(hrow + c4 * 2048) = hi;
-            *reinterpret_cast<uint4*>(hrow + GR_H_BYTES / 2 + c4 * 2048) = lo;
-          }
-          fence_async_smem();
+          for (int c = 0; c < 16; ++c) split_pair(h[2 * c], h[2 * c + 1], hr16[c], lr16[c]);
+          tmem_st16(th, hr16);
+          tmem_st16(th + 16, lr16);
+          tmem_st_wait();
+          fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.h_ready[d]);
         }
@@ -634,29 +645,54 @@ __global__ void __launch_bounds__(GR_THREADS, 2) gru_rec_tc_kernel(const GrParam
       }
     }
   } else {
-    // MMA issuer
+    // MMA issuer + xw loader
     const uint32_t idesc = make_idesc_f16(128, 96);
     const int nsplit = P.nsplit;
     uint32_t n_h = 0;
+    uint32_t n_ld[2] = {0, 0};          // slabs requested per direction
+    int64_t ld_tile[2] = {blockIdx.x, blockIdx.x};
+    int ld_s[2] = {0, 0};
+    auto load_next = [&](const int dd) {   // requests direction dd's next slab if its stage is free (never blocks)
+      if (ld_tile[dd] >= n_tiles) return;
+      const int xs = n_ld[dd] % GR_XST;
+      if (n_ld[dd] >= (uint32_t)GR_XST) {
+        uint32_t ok = 0;   // one lane probes, the result is broadcast (a per-lane probe could split the warp)
+        if (lane == 0) ok = mbar_test_wait(&sm.x_empty[dd][xs], ((n_ld[dd] / GR_XST) & 1) ^ 1) ? 1u : 0u;
+        if (!__shfl_sync(0xffffffffu, ok, 0)) return;
+      }
+      const int t = dd ? GR_T - 1 - ld_s[dd] : ld_s[dd];
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&sm.x_full[dd][xs], GR_X_BYTES);
+        bulk_g2s(sm.x[dd][xs], reinterpret_cast<const unsigned char*>(P.xw) + ((size_t)(ld_tile[dd] * GR_T + t) * 48 + dd * 24) * 128 * 16,
+                 GR_X_BYTES, &sm.x_full[dd][xs]);
+      }
+      ++n_ld[dd];
+      if (++ld_s[dd] == GR_T) { ld_s[dd] = 0; ld_tile[dd] += gridDim.x; }
+    };
+    load_next(0); load_next(1); load_next(0); load_next(1);
+    const uint64_t db0 = make_desc(smem_u32(sm.u[0]), 1536, 128), db1 = make_desc(smem_u32(sm.u[1]), 1536, 128);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int s = 1; s < GR_T; ++s, ++n_h) {
+#pragma unroll
         for (int d = 0; d < 2; ++d) {
+          load_next(0);
+          load_next(1);
           mbar_wait(&sm.h_ready[d], n_h & 1);
           fence_after_sync();
-          const uint32_t a_hi = smem_u32(sm.h[d]), a_lo = a_hi + GR_H_BYTES / 2;
-          const uint32_t b_hi = smem_u32(sm.u[d]), b_lo = b_hi + GR_U_BYTES / 2;
-          const uint32_t acc = tmem + d * 96;
+          if (elect_one()) {
+            const uint32_t acc = tmem + d * 96, ta = tmem + 192 + d * 32;
+            const uint64_t db = d ? db1 : db0;
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const uint64_t dah = make_desc(a_hi + kk * 4096, 2048, 128), dal = make_desc(a_lo + kk * 4096, 2048, 128);
-            const uint64_t dbh = make_desc(b_hi + kk * 3072, 1536, 128), dbl = make_desc(b_lo + kk * 3072, 1536, 128);
-            mma_f16_ss_w(acc, dah, dbh, idesc, kk != 0);
-            if (nsplit == 3) {
-              mma_f16_ss_w(acc, dal, dbh, idesc, true);
-              mma_f16_ss_w(acc, dah, dbl, idesc, true);
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t dbh = db + (uint64_t)((kk * 3072) >> 4), dbl = dbh + (uint64_t)((GR_U_BYTES / 2) >> 4);
+              mma_f16_ts(acc, ta + kk * 8, dbh, idesc, kk != 0);
+              if (nsplit == 3) {
+                mma_f16_ts(acc, ta + 16 + kk * 8, dbh, idesc, true);
+                mma_f16_ts(acc, ta + kk * 8, dbl, idesc, true);
+              }
             }
+            mma_commit(&sm.acc_full[d]);
           }
-          if (elect_one()) mma_commit(&sm.acc_full[d]);
           __syncwarp();
         }
       }
@@ -697,7 +733,7 @@ int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* 
   const size_t smem = sizeof(GrSmem) + 128;
   WWB_CUDA(ctx, cudaFuncSetAttribute(gru_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (B + 127) / 128;
-  const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 2 * (int64_t)ctx->sm_count);
+  const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count);
   gru_rec_tc_kernel<<<grid, GR_THREADS, smem, st>>>(P);
   WWB_CHECK_LAUNCH(ctx);
   return WWB_OK;

@@ -122,6 +122,12 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive that cannot be executed before `dep` is available: used to release a buffer only after the loads whose
+// results feed `dep` have completed
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint32_t dep) {
+  asm volatile("{\n\t.reg .b32 t;\n\tmov.b32 t, %1;\n\tmbarrier.arrive.shared::cta.b64 _, [%0];\n\t}\n" ::"r"(smem_u32(bar)), "r"(dep)
+               : "memory");
+}
 // try_wait with a suspend-time hint: without the hint the instruction returns after a few tens of
 // cycles and a waiting warp turns into a spin loop that competes for issue slots with the MMA
 // issuer and the epilogue warps of its scheduler (measured: 35 % of all issued instructions of
