@@ -177,10 +177,18 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
 int crnn_simt_detect(wwb_ctx* ctx, const float* enc, int64_t B, float* out, cudaStream_t st);
 std::vector<unsigned char> crnn_pack_conv(const float* conv_w);
 std::vector<unsigned char> crnn_pack_w1(const float* w_nk);
-int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st);
+// shared-column geometry of a sliding-window batch (crnn_tc.cu)
+struct CrnnShare {
+  int q, nsp, Mp, F, wps, tps;
+  int64_t n_streams;
+};
+bool crnn_share_plan(const WinMap& wm, int L, CrnnShare* out);
+size_t crnn_share_xws_bytes(const CrnnShare& g, int64_t n_streams);
+size_t crnn_share_xwb_bytes(const CrnnShare& g, int64_t n_streams);
+int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st, int mode = 0, const CrnnShare* g = nullptr);
 std::vector<unsigned char> crnn_pack_u(const float* u_f, const float* u_b);
 int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* last_out, int64_t B,
-               const int32_t* n_dev, cudaStream_t st);
+               const int32_t* n_dev, cudaStream_t st, const float* xws = nullptr, const CrnnShare* g = nullptr);
 int wavenet_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
                             float* post, cudaStream_t st);
 int wavenet_tc_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
@@ -210,6 +218,22 @@ __device__ __forceinline__ const float* win_row(const WinMap& wm, int64_t b, int
     start = (int)(b % wm.win_per_stream) * wm.hop;
   }
   int r = start + t;
+  if (r >= wm.ring) r -= wm.ring;
+  return wm.mel + (s * wm.ring + r) * (int64_t)kMel;
+}
+
+// win_row split in two: the window's stream / first mel row, and a row of that stream (ring-wrapped)
+__device__ __forceinline__ void win_origin(const WinMap& wm, int64_t b, int64_t& s, int& start) {
+  b += wm.b0;
+  if (wm.win_stream) {
+    s = wm.win_stream[b];
+    start = wm.win_start[b];
+  } else {
+    s = b / wm.win_per_stream;
+    start = (int)(b % wm.win_per_stream) * wm.hop;
+  }
+}
+__device__ __forceinline__ const float* stream_row(const WinMap& wm, int64_t s, int r) {
   if (r >= wm.ring) r -= wm.ring;
   return wm.mel + (s * wm.ring + r) * (int64_t)kMel;
 }

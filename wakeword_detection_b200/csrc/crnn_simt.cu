@@ -7,6 +7,8 @@
 //   proj   : [B*19, in] x [in, 192] + b_in     (both directions side by side)
 //   gru    : 19 recurrent steps per direction, gates z|r|h, reset_after
 //   detect : 64 -> 64 ReLU -> n_out, sigmoid / softmax
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wwb {
@@ -211,14 +213,32 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
   const int64_t B = wm.n_win;
   if (B == 0) return WWB_OK;
   const CrnnWeights& W = ctx->crnn;
-  // chunk the batch so the conv intermediate stays bounded (48.6 KB per window)
-  // a multiple of 128 windows x 2 CTAs x 148 SMs (the recurrence kernel's wave)
-  const int64_t chunk = 37888;
-  void *conv = nullptr, *xw, *s1, *enc_ws;
+  // chunk the batch so the intermediates stay bounded (xw: 14.6 KB per window)
+  // a multiple of 128 windows x 148 SMs (the recurrence kernel's wave)
+  int64_t chunk = 37888;
+  // sliding-window batches on the tensor-core path share the conv / GRU-1 projection columns between windows
+  // (crnn_tc.cu, CrnnShare); chunks are then whole streams
+  CrnnShare sh;
+  // (WWB_CRNN_NO_SHARE=1 forces the per-window path: used by the tests to check that both give identical bits)
+  const char* no_share = getenv("WWB_CRNN_NO_SHARE");
+  const bool shared = ctx->precision != WWB_PREC_F32 && !(no_share && no_share[0] == '1') && crnn_share_plan(wm, ctx->L, &sh);
+  int64_t chunk_streams = 0;
+  if (shared) {
+    chunk_streams = std::max<int64_t>(1, chunk / sh.wps);
+    // whole waves of the layer-1 recurrence (tps tiles per stream) when the batch is large enough
+    const int64_t wave_streams = std::max<int64_t>(1, ctx->sm_count / sh.tps);
+    if (chunk_streams > wave_streams && ctx->sm_count % sh.tps == 0) chunk_streams -= chunk_streams % wave_streams;
+    chunk_streams = std::min(chunk_streams, sh.n_streams);
+    chunk = chunk_streams * sh.wps;
+  }
+  void *conv = nullptr, *xw, *s1, *enc_ws, *xws = nullptr;
   int rc;
   // the 48.6 KB/window conv intermediate exists only on the fp32 validation path (1.8 GB per chunk)
   if (ctx->precision == WWB_PREC_F32 && (rc = workspace(ctx, 1, (size_t)std::min(B, chunk) * C_T * C_FEAT * 4, &conv))) return rc;
-  if ((rc = workspace(ctx, 2, (size_t)((std::min(B, chunk) + 127) / 128 * 128) * C_T * 2 * C_G * 4, &xw))) return rc;
+  if (shared && (rc = workspace(ctx, 1, crnn_share_xws_bytes(sh, chunk_streams), &xws))) return rc;
+  size_t xw_bytes = (size_t)((std::min(B, chunk) + 127) / 128 * 128) * C_T * 2 * C_G * 4;
+  if (shared) xw_bytes = std::max(xw_bytes, crnn_share_xwb_bytes(sh, chunk_streams));
+  if ((rc = workspace(ctx, 2, xw_bytes, &xw))) return rc;
   if ((rc = workspace(ctx, 3, (size_t)std::min(B, chunk) * C_T * 64 * 4, &s1))) return rc;
   if ((rc = workspace(ctx, 4, (size_t)std::min(B, chunk) * 64 * 4, &enc_ws))) return rc;
   if (wm.n_win_dev && B > chunk) return fail(ctx, WWB_ERR_ARG, "streaming batch too large");
@@ -227,12 +247,19 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
     WinMap sub = wm;
     sub.n_win = nb;
     sub.b0 = wm.b0 + b0;
+    if (shared) {   // the chunk's streams become streams 0.. of the sub-batch
+      sub.mel = wm.mel + (b0 / sh.wps) * (int64_t)wm.ring * kMel;
+      sub.b0 = 0;
+    }
     float* enc = enc_out ? enc_out + b0 * 64 : (float*)enc_ws;
     const int64_t M = nb * C_T;
     // both directions of a layer share one GEMM: Wt = [in][192]
     const bool tc = ctx->precision != WWB_PREC_F32;
     const int nsplit = ctx->precision == WWB_PREC_TC ? 3 : 1;
-    if (tc) {
+    if (shared) {
+      if ((rc = crnn_front_tc(ctx, sub, (float*)xws, st, 1, &sh))) return rc;   // interior columns, once per position
+      if ((rc = crnn_front_tc(ctx, sub, (float*)xw, st, 2, &sh))) return rc;    // padded columns t = 0 / 18 per window
+    } else if (tc) {
       if ((rc = crnn_front_tc(ctx, sub, (float*)xw, st))) return rc;
     } else {
       crnn_conv_kernel<<<(unsigned)nb, 256, 0, st>>>(sub, W.conv_w, W.conv_b, (float*)conv, ctx->L);
@@ -242,7 +269,7 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
       WWB_CHECK_LAUNCH(ctx);
     }
     if (tc) {
-      if ((rc = gru_rec_tc(ctx, 0, (float*)xw, (float*)s1, nullptr, nb, wm.n_win_dev, st))) return rc;
+      if ((rc = gru_rec_tc(ctx, 0, (float*)xw, (float*)s1, nullptr, nb, wm.n_win_dev, st, (float*)xws, &sh))) return rc;
       if ((rc = tc_gemm_bias(ctx, (float*)s1, W.gemm_b[1], W.tc_bi[1], (float*)xw, M, 64, nsplit, 1, st))) return rc;
       if ((rc = gru_rec_tc(ctx, 1, (float*)xw, nullptr, enc, nb, wm.n_win_dev, st))) return rc;
     } else {

@@ -61,15 +61,34 @@ struct CaSmem {
   uint32_t tmem_base;
 };
 
+// Sliding-window batches (regular grid, hop h in {1,2,4,8}) share conv columns between windows: the conv's time stride
+// is 8 frames, so column t of window j covers frames h*j + 8t - 6 .. + 13 and depends only on the POSITION INDEX
+// m = j + q*t (q = 8/h) as long as it does not touch the window's zero padding, i.e. for t = 1..17.  Those columns (and
+// their 192-wide GRU-1 input projection) are computed once per stream and position by tiles that are STRIPS of 126
+// consecutive conv steps of one stream and phase (mode 1); the two padded columns t = 0 / 18 of every window are
+// computed by tiles of 21 windows with 6 row slots each (mode 2).  Each column is the same MMA sequence on the same
+// operands as in mode 0, so the results are bit-identical.
+//   xwS: [stream][48 float4 columns][Mp positions]            (interior columns, mode 1)
+//   xwB: [recurrence tile = stream*tps + j/128][2][48][128]   (t = 0 and t = 18, mode 2)
+enum { CA_MODE_WINDOWS = 0, CA_MODE_STRIPS = 1, CA_MODE_BOUNDARY = 2 };
+constexpr int CA_STRIP_ROWS = 126, CA_BWIN = 21, CA_BSLOTS = 6;
+// geometry: CrnnShare (common.cuh): q = position indices per conv step (8 / hop), nsp = strips per stream and phase,
+// Mp = positions per xwS column row (q * 126 * nsp), F = frames of a stream covered by windows, wps = windows per
+// stream, tps = recurrence tiles per stream
+using CaShare = CrnnShare;
+
 struct CaParams {
   WinMap wm;
   const unsigned char* cw;      // packed conv weights (2 planes)
   const unsigned char* w1;      // [20][CA_W1_SLICE]
   const float* conv_b;
   const float* b_in;            // [192]
-  float* xw1;                   // [ceil(n_win/128), 19, 48, 128] float4 (see the projection epilogue)
+  float* xw1;                   // mode 0: [ceil(n_win/128), 19, 48, 128] float4 (see the projection epilogue); modes 1/2: see CaShare
   int L;
   int nsplit;
+  int mode;                     // CA_MODE_*
+  int64_t n_tiles;              // modes 1/2 (mode 0 derives it from the window count)
+  CaShare sh;
   long long* dbg;               // optional issuer timeline of the CTA's second tile: [20 f][8 events]
 };
 
@@ -88,7 +107,8 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role branches are uniform branches
   const int64_t n_win = P.wm.n_win_dev ? (int64_t)*P.wm.n_win_dev : P.wm.n_win;
-  const int64_t n_tiles = (n_win + CA_WPT - 1) / CA_WPT;
+  const int mode = P.mode;
+  const int64_t n_tiles = mode == CA_MODE_WINDOWS ? (n_win + CA_WPT - 1) / CA_WPT : P.n_tiles;
 
   // ---- one-time setup ----
   for (int i = tid; i < (int)(sizeof(sm.xp) / 16); i += CA_THREADS) reinterpret_cast<uint4*>(sm.xp)[i] = make_uint4(0, 0, 0, 0);
@@ -150,22 +170,44 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
     // otherwise stall the conv epilogue — and with it the tensor pipe — for ~10k cycles per tile.
     // xw layout: [tile of 128 windows][t][48 float4 columns][128 windows]: the recurrence kernel
     // (one thread per window) reads it fully coalesced.
-    auto proj_chunk = [&](int64_t pb_b, bool pvalid, int pbuf, int c0) {
+    const int64_t cstride = mode == CA_MODE_STRIPS ? P.sh.Mp : 128;   // float4 between two columns of a row's xw
+    auto proj_chunk = [&](int64_t pbase, bool pvalid, int pbuf, int c0) {
       float v[16];
       tmem_ld16(tlane + TM_PACC + pbuf * 192 + c0, v);
       tmem_ld_wait();
       if (pvalid) {
-        float4* dst = reinterpret_cast<float4*>(P.xw1) + (((pb_b >> 7) * CA_T + t) * 48 + c0 / 4) * 128 + (pb_b & 127);
+        float4* dst = reinterpret_cast<float4*>(P.xw1) + pbase + (c0 / 4) * cstride;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          dst[i * 128] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);   // b_in was added by the tensor core
+          dst[i * cstride] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);   // b_in was added by the tensor core
       }
     };
     int64_t prev_b = 0;
     bool prev_valid = false, have_prev = false;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-      const int64_t b = tile * CA_WPT + wl;
-      const bool valid = (wl < CA_WPT) && (t < CA_T) && (b < n_win);
+      // where this row's 48 float4 of xw go (index of column 0) and whether the row is real
+      int64_t b;
+      bool valid;
+      if (mode == CA_MODE_WINDOWS) {
+        const int64_t w = tile * CA_WPT + wl;
+        valid = (wl < CA_WPT) && (t < CA_T) && (w < n_win);
+        b = (((w >> 7) * CA_T + t) * 48) * 128 + (w & 127);
+      } else if (mode == CA_MODE_STRIPS) {
+        const int per = P.sh.q * P.sh.nsp;
+        const int64_t stream = tile / per;
+        const int rem = (int)(tile - stream * per);
+        const int k = rem / P.sh.q, phase = rem - k * P.sh.q;
+        const int m = phase + P.sh.q * (CA_STRIP_ROWS * k + r);
+        valid = r < CA_STRIP_ROWS;
+        b = stream * 48 * P.sh.Mp + m;
+      } else {
+        const int wl2 = r / CA_BSLOTS, slot = r - wl2 * CA_BSLOTS;
+        const int64_t w = tile * CA_BWIN + wl2;
+        valid = (slot == 0 || slot == 3) && wl2 < CA_BWIN && w < n_win;
+        const int64_t stream = w / P.sh.wps;
+        const int j = (int)(w - stream * P.sh.wps);
+        b = (((stream * P.sh.tps + (j >> 7)) * 2 + (slot == 3)) * 48) * 128 + (j & 127);
+      }
       for (int f = 0; f < CA_F; ++f) {
         const uint32_t ci = tcount * CA_F + f;
         const int cb = ci % CA_CR;
@@ -351,13 +393,36 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
     // =========================== XP producers ===========================
     const int pset = (warp - (CA_EPI_WARPS + CA_ROLE_WARPS)) / CA_PROD_WARPS;       // this set fills the groups with gg % 2 == pset
     const int task = tid - (CA_EPI_WARPS + CA_ROLE_WARPS + pset * CA_PROD_WARPS) * 32;   // 0..127; element e = task
-    const int wl = task / CA_TP, c = task - wl * CA_TP;  // window in tile, time chunk (frames 8c-6 .. 8c+1)
-    const bool has_task = task < CA_WPT * CA_TP;
-    const int L = P.L;
+    const bool has_task = mode == CA_MODE_WINDOWS ? task < CA_WPT * CA_TP : true;
     uint32_t gg = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t b = tile * CA_WPT + wl;
-      const bool live = has_task && b < n_win;
+      // element `task` of the tile = 8 consecutive frames f0 .. f0+7 (relative to `start` of stream s), valid in [0, fhi)
+      int64_t s = 0;
+      int start = 0, f0, fhi;
+      bool live;
+      if (mode == CA_MODE_WINDOWS) {
+        const int wl = task / CA_TP, c = task - wl * CA_TP;   // window in tile, time chunk (frames 8c-6 .. 8c+1)
+        const int64_t b = tile * CA_WPT + wl;
+        live = has_task && b < n_win;
+        if (live) win_origin(P.wm, b, s, start);
+        f0 = 8 * c - 6;
+        fhi = P.L;
+      } else if (mode == CA_MODE_STRIPS) {
+        const int per = P.sh.q * P.sh.nsp;
+        s = tile / per;
+        const int rem = (int)(tile - s * per);
+        const int k = rem / P.sh.q, phase = rem - k * P.sh.q;
+        live = true;
+        f0 = (8 / P.sh.q) * phase + 8 * (CA_STRIP_ROWS * k + task) - 6;
+        fhi = P.sh.F;
+      } else {
+        const int wl2 = task / CA_BSLOTS, c = task - wl2 * CA_BSLOTS;   // chunks 0..2: column t = 0, chunks 3..5: column t = 18
+        const int64_t b = tile * CA_BWIN + wl2;
+        live = wl2 < CA_BWIN && b < n_win;
+        if (live) win_origin(P.wm, b, s, start);
+        f0 = (c < 3 ? 8 * c : 8 * (CA_T - 1) + 8 * (c - 3)) - 6;
+        fhi = P.L;
+      }
       for (int g = 0; g < CA_GROUPS; ++g, ++gg) {
         if ((int)(gg & 1) != pset) continue;
         const int slot = gg % 3;
@@ -366,9 +431,9 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         const bool data = live && g >= 1 && g <= 5;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int frame = 8 * c - 6 + i;
-          if (data && frame >= 0 && frame < L) {
-            const float4* src = reinterpret_cast<const float4*>(win_row(P.wm, b, frame) + 8 * (g - 1));
+          const int frame = f0 + i;
+          if (data && frame >= 0 && frame < fhi) {
+            const float4* src = reinterpret_cast<const float4*>(stream_row(P.wm, s, start + frame) + 8 * (g - 1));
             v[i][0] = __ldg(src);
             v[i][1] = __ldg(src + 1);
           } else {
@@ -443,9 +508,43 @@ std::vector<unsigned char> crnn_pack_w1(const float* w_nk) {
   return out;
 }
 
-int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st) {
+// geometry of the shared-column path for a regular window grid; false if the grid does not qualify
+bool crnn_share_plan(const WinMap& wm, int L, CrnnShare* out) {
+  if (wm.win_stream || wm.n_win_dev || wm.b0 != 0 || wm.win_per_stream < 2) return false;
+  const int hop = wm.hop;
+  if (hop != 1 && hop != 2 && hop != 4 && hop != 8) return false;
+  const int wps = wm.win_per_stream;
+  if (wm.n_win % wps) return false;
+  if ((int64_t)(wps - 1) * hop + L > wm.ring) return false;   // a window would wrap around the ring
+  CrnnShare g;
+  g.q = 8 / hop;
+  g.wps = wps;
+  g.tps = (wps + 127) / 128;
+  g.F = (wps - 1) * hop + L;
+  const int m_max = wps - 1 + 17 * g.q;
+  g.nsp = (m_max / g.q + 1 + CA_STRIP_ROWS - 1) / CA_STRIP_ROWS;
+  g.Mp = g.q * CA_STRIP_ROWS * g.nsp;
+  g.n_streams = wm.n_win / wps;
+  // worth it only if it is fewer tiles than 6 windows per tile
+  const int64_t tiles_shared = g.n_streams * g.q * g.nsp + (wm.n_win + CA_BWIN - 1) / CA_BWIN;
+  if (tiles_shared >= (wm.n_win + CA_WPT - 1) / CA_WPT) return false;
+  *out = g;
+  return true;
+}
+size_t crnn_share_xws_bytes(const CrnnShare& g, int64_t n_streams) { return ((size_t)n_streams * 48 * g.Mp + 256) * 16; }
+size_t crnn_share_xwb_bytes(const CrnnShare& g, int64_t n_streams) { return (size_t)n_streams * g.tps * 2 * 48 * 128 * 16; }
+
+int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st, int mode, const CrnnShare* g) {
   if (wm.n_win == 0) return WWB_OK;
   CaParams P;
+  memset(&P, 0, sizeof(P));
+  P.mode = mode;
+  int64_t n_tiles = (wm.n_win + CA_WPT - 1) / CA_WPT;
+  if (mode != CA_MODE_WINDOWS) {
+    P.sh = *g;
+    n_tiles = mode == CA_MODE_STRIPS ? (wm.n_win / g->wps) * g->q * g->nsp : (wm.n_win + CA_BWIN - 1) / CA_BWIN;
+  }
+  P.n_tiles = n_tiles;
   P.wm = wm;
   P.cw = ctx->crnn.tc_conv;
   P.w1 = ctx->crnn.tc_w1;
@@ -457,7 +556,6 @@ int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st) {
   P.dbg = reinterpret_cast<long long*>(ctx->debug_buf);
   const size_t smem = sizeof(CaSmem) + 128;
   WWB_CUDA(ctx, cudaFuncSetAttribute(crnn_front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t n_tiles = (wm.n_win + CA_WPT - 1) / CA_WPT;
   const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, ctx->sm_count);
   crnn_front_tc_kernel<<<grid, CA_THREADS, smem, st>>>(P);
   WWB_CHECK_LAUNCH(ctx);
@@ -500,7 +598,10 @@ struct GrSmem {
 };
 
 struct GrParams {
-  const float* xw;              // [ceil(B/128), 19, 48, 128] float4
+  const float* xw;              // [ceil(B/128), 19, 48, 128] float4 (shared-column mode: xwB, [tile][2][48][128])
+  const float* xws;             // shared-column mode: interior columns [stream][48][Mp] float4, else null
+  int q, Mp, wps, tps;          // shared-column geometry (CaShare); tiles are then per stream: tile = stream*tps + j/128
+  int64_t n_tiles;
   const unsigned char* u;       // [2][GR_U_BYTES] packed
   const float* bh;              // [2][32]  recurrent bias of the candidate gate
   float* seq_out;               // [B, 19, 64] or null
@@ -539,7 +640,8 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role branches are uniform branches
   const int64_t n_win = P.n_win_dev ? (int64_t)*P.n_win_dev : P.n_win;
-  const int64_t n_tiles = (n_win + 127) / 128;
+  const bool shared = P.xws != nullptr;
+  const int64_t n_tiles = shared ? P.n_tiles : (n_win + 127) / 128;
 
   for (int i = tid; i < (int)(2 * GR_U_BYTES / 16); i += GR_THREADS)
     reinterpret_cast<uint4*>(&sm.u[0][0])[i] = reinterpret_cast<const uint4*>(P.u)[i];
@@ -566,8 +668,14 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
     const float* bh = sm.bh[d];
     uint32_t n_acc = 0, n_x = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t b = tile * 128 + r;
-      const bool valid = b < n_win;
+      int64_t b = tile * 128 + r;
+      bool valid = b < n_win;
+      if (shared) {
+        const int64_t stream = tile / P.tps;
+        const int j = (int)(tile - stream * P.tps) * 128 + r;
+        b = stream * P.wps + j;
+        valid = j < P.wps;
+      }
       float h[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) h[i] = 0.f;
@@ -661,10 +769,20 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
         if (!__shfl_sync(0xffffffffu, ok, 0)) return;
       }
       const int t = dd ? GR_T - 1 - ld_s[dd] : ld_s[dd];
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&sm.x_full[dd][xs], GR_X_BYTES);
-        bulk_g2s(sm.x[dd][xs], reinterpret_cast<const unsigned char*>(P.xw) + ((size_t)(ld_tile[dd] * GR_T + t) * 48 + dd * 24) * 128 * 16,
-                 GR_X_BYTES, &sm.x_full[dd][xs]);
+      if (lane == 0) mbar_arrive_expect_tx(&sm.x_full[dd][xs], GR_X_BYTES);
+      __syncwarp();
+      if (shared && t != 0 && t != GR_T - 1) {
+        // interior column: 128 consecutive positions (windows j0.. at step t sit at m = j0 + q*t ..) of 24 column rows
+        const int64_t stream = ld_tile[dd] / P.tps;
+        const int j0 = (int)(ld_tile[dd] - stream * P.tps) * 128;
+        if (lane < 24)
+          bulk_g2s(sm.x[dd][xs] + lane * 2048,
+                   reinterpret_cast<const unsigned char*>(P.xws) + (((size_t)stream * 48 + dd * 24 + lane) * P.Mp + j0 + P.q * t) * 16,
+                   2048, &sm.x_full[dd][xs]);
+      } else if (lane == 0) {
+        const size_t slab = shared ? (size_t)ld_tile[dd] * 2 + (t != 0) : (size_t)ld_tile[dd] * GR_T + t;
+        bulk_g2s(sm.x[dd][xs], reinterpret_cast<const unsigned char*>(P.xw) + (slab * 48 + dd * 24) * 128 * 16, GR_X_BYTES,
+                 &sm.x_full[dd][xs]);
       }
       ++n_ld[dd];
       if (++ld_s[dd] == GR_T) { ld_s[dd] = 0; ld_tile[dd] += gridDim.x; }
@@ -719,10 +837,18 @@ std::vector<unsigned char> crnn_pack_u(const float* u_f, const float* u_b) {
 }
 
 int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* last_out, int64_t B,
-               const int32_t* n_dev, cudaStream_t st) {
+               const int32_t* n_dev, cudaStream_t st, const float* xws, const CrnnShare* g) {
   if (B == 0) return WWB_OK;
   GrParams P;
+  memset(&P, 0, sizeof(P));
   P.xw = xw;
+  int64_t n_tiles = (B + 127) / 128;
+  if (xws) {
+    P.xws = xws;
+    P.q = g->q; P.Mp = g->Mp; P.wps = g->wps; P.tps = g->tps;
+    n_tiles = (B / g->wps) * g->tps;
+  }
+  P.n_tiles = n_tiles;
   P.u = ctx->crnn.tc_u[layer];
   P.bh = ctx->crnn.tc_bh[layer];
   P.seq_out = seq_out;
@@ -732,7 +858,6 @@ int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* 
   P.nsplit = ctx->precision == WWB_PREC_TC ? 3 : 1;
   const size_t smem = sizeof(GrSmem) + 128;
   WWB_CUDA(ctx, cudaFuncSetAttribute(gru_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t n_tiles = (B + 127) / 128;
   const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count);
   gru_rec_tc_kernel<<<grid, GR_THREADS, smem, st>>>(P);
   WWB_CHECK_LAUNCH(ctx);
