@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import numpy as np, torch
 from conftest import get_engine
-tc = get_engine("CRNN", "tc")
+tc = get_engine("CRNN", "tc"); f32 = get_engine("CRNN", "f32")
 ok = True
 for (S, F, hop) in [(3, 200, 2), (2, 151 + 2 * 130, 2), (5, 998, 2), (2, 700, 1), (3, 600, 4), (2, 1200, 8), (1, 153, 2), (7, 2000, 2), (90, 998, 2)]:
     torch.manual_seed(S * 1000 + F)
@@ -14,6 +14,10 @@ for (S, F, hop) in [(3, 200, 2), (2, 151 + 2 * 130, 2), (5, 998, 2), (2, 700, 1)
     b = tc.posteriors(X, hop=hop).clone(); torch.cuda.synchronize()
     b2 = tc.posteriors(X, hop=hop).clone(); torch.cuda.synchronize()
     d = (a - b).abs().max().item()
+    ref = f32.posteriors(X, hop=hop)
+    e = (b - ref).abs().max().item()
+    ok &= e < 1e-4
+    print("   vs fp32 path: max err %.3e" % e)
     same = bool((a == b).all().item()) and bool((b == b2).all().item())
     ok &= same
     print("S=%d F=%d hop=%d n_win=%d: max |diff| %.3e bit-identical=%s" % (S, F, hop, a.shape[1], d, same), flush=True)

@@ -154,6 +154,7 @@ static int build_crnn(wwb_ctx* ctx, const wwb_weights* w) {
         memcpy(&w_nk[(size_t)dir * 96 * in], w->gru_w[layer * 2 + dir], sizeof(float) * 96 * in);
       if ((rc = upload(ctx, pack_gemm_b(w_nk.data(), in, true), &C.gemm_b[layer]))) return rc;
       if (layer == 0 && (rc = upload(ctx, crnn_pack_w1(w_nk.data()), &C.tc_w1))) return rc;
+      if (layer == 1 && (rc = upload(ctx, crnn_pack_w2(w_nk.data()), &C.tc_w2))) return rc;
     }
     {  // tensor-core recurrence: packed U, candidate-gate bias, input bias with the z/r recurrent bias folded in
       if ((rc = upload(ctx, crnn_pack_u(w->gru_u[layer * 2], w->gru_u[layer * 2 + 1]), &C.tc_u[layer]))) return rc;
@@ -166,6 +167,7 @@ static int build_crnn(wwb_ctx* ctx, const wwb_weights* w) {
         }
       if ((rc = upload(ctx, bh, &C.tc_bh[layer]))) return rc;
       if ((rc = upload(ctx, bf, &C.tc_bi[layer]))) return rc;
+      if (layer == 1 && (rc = upload(ctx, crnn_reorder_bias2(bf.data()), &C.tc_bi2))) return rc;
     }
     for (int dir = 0; dir < 2; ++dir) {
       if ((rc = upload(ctx, transposed(w->gru_u[layer * 2 + dir], 96, 32), &C.gru_u[layer * 2 + dir]))) return rc;

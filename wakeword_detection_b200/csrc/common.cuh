@@ -49,6 +49,8 @@ struct CrnnWeights {   // device copies, fp32, layouts chosen for the kernels
   unsigned char* tc_u[2] = {};        // crnn_tc.cu: packed recurrent weights, both directions, per layer
   float* tc_bh[2] = {};               // [2][32] recurrent bias of the candidate gate, per layer
   float* tc_bi[2] = {};               // [192] b_in with the z/r parts of the recurrent bias folded in
+  unsigned char* tc_w2 = nullptr;     // crnn_tc.cu: layer-2 input projection packed for the fused layer-2 kernel
+  float* tc_bi2 = nullptr;            // [2][96] tc_bi[1] in that kernel's accumulator column order
 };
 
 struct WavenetWeights {
@@ -188,7 +190,13 @@ size_t crnn_share_xwb_bytes(const CrnnShare& g, int64_t n_streams);
 int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st, int mode = 0, const CrnnShare* g = nullptr);
 std::vector<unsigned char> crnn_pack_u(const float* u_f, const float* u_b);
 int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* last_out, int64_t B,
-               const int32_t* n_dev, cudaStream_t st, const float* xws = nullptr, const CrnnShare* g = nullptr);
+               const int32_t* n_dev, cudaStream_t st, const float* xws = nullptr, const CrnnShare* g = nullptr,
+               unsigned char* seq_packed = nullptr);
+std::vector<unsigned char> crnn_pack_w2(const float* w_nk);
+std::vector<float> crnn_reorder_bias2(const float* bf);
+size_t crnn_seq_packed_bytes(int64_t B);
+int gru2_fused_tc(wwb_ctx* ctx, const unsigned char* seq_packed, float* last_out, int64_t B, const int32_t* n_dev,
+                  cudaStream_t st);
 int wavenet_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
                             float* post, cudaStream_t st);
 int wavenet_tc_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,

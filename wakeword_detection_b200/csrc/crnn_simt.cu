@@ -239,7 +239,8 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
   size_t xw_bytes = (size_t)((std::min(B, chunk) + 127) / 128 * 128) * C_T * 2 * C_G * 4;
   if (shared) xw_bytes = std::max(xw_bytes, crnn_share_xwb_bytes(sh, chunk_streams));
   if ((rc = workspace(ctx, 2, xw_bytes, &xw))) return rc;
-  if ((rc = workspace(ctx, 3, (size_t)std::min(B, chunk) * C_T * 64 * 4, &s1))) return rc;
+  // layer-1 output: fp32 [B, 19, 64] (fp32 path) or the packed fp16 hi/lo operand of the fused layer-2 kernel (same bytes per value)
+  if ((rc = workspace(ctx, 3, std::max((size_t)std::min(B, chunk) * C_T * 64 * 4, crnn_seq_packed_bytes(std::min(B, chunk))), &s1))) return rc;
   if ((rc = workspace(ctx, 4, (size_t)std::min(B, chunk) * 64 * 4, &enc_ws))) return rc;
   if (wm.n_win_dev && B > chunk) return fail(ctx, WWB_ERR_ARG, "streaming batch too large");
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
@@ -268,7 +269,12 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
                                                                             (float*)xw, M, 2 * C_G, C_FEAT);
       WWB_CHECK_LAUNCH(ctx);
     }
-    if (tc) {
+    const char* no_fuse = getenv("WWB_CRNN_NO_FUSE2");
+    if (tc && !(no_fuse && no_fuse[0] == '1')) {
+      // layer 1 leaves its output as the packed A operand of layer 2's input projection, which the layer-2 kernel computes itself
+      if ((rc = gru_rec_tc(ctx, 0, (float*)xw, nullptr, nullptr, nb, wm.n_win_dev, st, (float*)xws, &sh, (unsigned char*)s1))) return rc;
+      if ((rc = gru2_fused_tc(ctx, (unsigned char*)s1, enc, nb, wm.n_win_dev, st))) return rc;
+    } else if (tc) {
       if ((rc = gru_rec_tc(ctx, 0, (float*)xw, (float*)s1, nullptr, nb, wm.n_win_dev, st, (float*)xws, &sh))) return rc;
       if ((rc = tc_gemm_bias(ctx, (float*)s1, W.gemm_b[1], W.tc_bi[1], (float*)xw, M, 64, nsplit, 1, st))) return rc;
       if ((rc = gru_rec_tc(ctx, 1, (float*)xw, nullptr, enc, nb, wm.n_win_dev, st))) return rc;

@@ -66,12 +66,15 @@ struct CaSmem {
 // m = j + q*t (q = 8/h) as long as it does not touch the window's zero padding, i.e. for t = 1..17.  Those columns (and
 // their 192-wide GRU-1 input projection) are computed once per stream and position by tiles that are STRIPS of 126
 // consecutive conv steps of one stream and phase (mode 1); the two padded columns t = 0 / 18 of every window are
-// computed by tiles of 21 windows with 6 row slots each (mode 2).  Each column is the same MMA sequence on the same
+// computed by tiles of 25 windows with 5 elements each (mode 2): [A0 A1 A2 B0 B1], A = frames -6..17 (column t = 0,
+// row slot 0), B = frames 138..153 (column t = 18, row slot 3).  Column 18's third chunk (frames 154..161, all padding)
+// is whatever element follows - the next window's A0, whose first six values are zero padding and whose last two meet
+// the zero weights of the (non-existent) time taps 22 and 23: it contributes exactly 0.  Each column is the same MMA sequence on the same
 // operands as in mode 0, so the results are bit-identical.
 //   xwS: [stream][48 float4 columns][Mp positions]            (interior columns, mode 1)
 //   xwB: [recurrence tile = stream*tps + j/128][2][48][128]   (t = 0 and t = 18, mode 2)
 enum { CA_MODE_WINDOWS = 0, CA_MODE_STRIPS = 1, CA_MODE_BOUNDARY = 2 };
-constexpr int CA_STRIP_ROWS = 126, CA_BWIN = 21, CA_BSLOTS = 6;
+constexpr int CA_STRIP_ROWS = 126, CA_BWIN = 25, CA_BSLOTS = 5;
 // geometry: CrnnShare (common.cuh): q = position indices per conv step (8 / hop), nsp = strips per stream and phase,
 // Mp = positions per xwS column row (q * 126 * nsp), F = frames of a stream covered by windows, wps = windows per
 // stream, tps = recurrence tiles per stream
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         f0 = (8 / P.sh.q) * phase + 8 * (CA_STRIP_ROWS * k + task) - 6;
         fhi = P.sh.F;
       } else {
-        const int wl2 = task / CA_BSLOTS, c = task - wl2 * CA_BSLOTS;   // chunks 0..2: column t = 0, chunks 3..5: column t = 18
+        const int wl2 = task / CA_BSLOTS, c = task - wl2 * CA_BSLOTS;   // chunks 0..2: column t = 0, chunks 3..4: column t = 18
         const int64_t b = tile * CA_BWIN + wl2;
         live = wl2 < CA_BWIN && b < n_win;
         if (live) win_origin(P.wm, b, s, start);
@@ -583,6 +586,7 @@ constexpr int GR_H_BYTES = 2 * 4 * 128 * 16;     // hi + lo planes, K = 32
 constexpr int GR_U_BYTES = 2 * 4 * 96 * 16;
 constexpr int GR_THREADS = 9 * 32;
 
+constexpr int G2_A_BYTES = 2 * 8 * 128 * 16;       // layer-1 output of 128 windows at one step as a packed fp16 hi/lo operand (K = 64): 32 KB
 constexpr int GR_X_BYTES = 24 * 128 * 16;          // one direction's xw of one step: 24 float4 columns x 128 windows (contiguous in HBM)
 constexpr int GR_XST = 2;                          // xw stages PER DIRECTION (a stage never changes its consumer warps)
 
@@ -605,6 +609,8 @@ struct GrParams {
   const unsigned char* u;       // [2][GR_U_BYTES] packed
   const float* bh;              // [2][32]  recurrent bias of the candidate gate
   float* seq_out;               // [B, 19, 64] or null
+  unsigned char* seq_packed;    // or null: the layer's output sequence as the fp16 hi/lo A operand of the next layer's input
+                                // projection, [ceil(B/128)][19][plane hi, lo][8 chunks][128 windows][8 halves] (gru2_fused_tc_kernel)
   float* last_out;              // [B, 64] or null
   int64_t n_win;
   const int32_t* n_win_dev;
@@ -728,11 +734,11 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
           tok = __reduce_or_sync(0xffffffffu, tok);
           if (lane == 0) mbar_arrive_after(&sm.x_empty[d][xs], tok);
         }
+        uint32_t hr16[16], lr16[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) split_pair(h[2 * c], h[2 * c + 1], hr16[c], lr16[c]);
         if (s < GR_T - 1) {
           fence_before_sync();
-          uint32_t hr16[16], lr16[16];
-#pragma unroll
-          for (int c = 0; c < 16; ++c) split_pair(h[2 * c], h[2 * c + 1], hr16[c], lr16[c]);
           tmem_st16(th, hr16);
           tmem_st16(th + 16, lr16);
           tmem_st_wait();
@@ -744,6 +750,14 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
           float4* dst = reinterpret_cast<float4*>(P.seq_out + (b * GR_T + t) * 64 + d * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+        }
+        if (valid && P.seq_packed) {   // the split computed for the recurrent GEMM is the next layer's A operand: 512 contiguous bytes per warp store
+          unsigned char* dst = P.seq_packed + ((size_t)((b >> 7) * GR_T + t) * G2_A_BYTES) + (size_t)((d * 4) * 128 + (int)(b & 127)) * 16;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            *reinterpret_cast<uint4*>(dst + u * 2048) = make_uint4(hr16[4 * u], hr16[4 * u + 1], hr16[4 * u + 2], hr16[4 * u + 3]);
+            *reinterpret_cast<uint4*>(dst + G2_A_BYTES / 2 + u * 2048) = make_uint4(lr16[4 * u], lr16[4 * u + 1], lr16[4 * u + 2], lr16[4 * u + 3]);
+          }
         }
       }
       if (valid && P.last_out) {
@@ -837,7 +851,7 @@ std::vector<unsigned char> crnn_pack_u(const float* u_f, const float* u_b) {
 }
 
 int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* last_out, int64_t B,
-               const int32_t* n_dev, cudaStream_t st, const float* xws, const CrnnShare* g) {
+               const int32_t* n_dev, cudaStream_t st, const float* xws, const CrnnShare* g, unsigned char* seq_packed) {
   if (B == 0) return WWB_OK;
   GrParams P;
   memset(&P, 0, sizeof(P));
@@ -852,6 +866,7 @@ int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* 
   P.u = ctx->crnn.tc_u[layer];
   P.bh = ctx->crnn.tc_bh[layer];
   P.seq_out = seq_out;
+  P.seq_packed = seq_packed;
   P.last_out = last_out;
   P.n_win = B;
   P.n_win_dev = n_dev;
@@ -860,6 +875,286 @@ int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* 
   WWB_CUDA(ctx, cudaFuncSetAttribute(gru_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count);
   gru_rec_tc_kernel<<<grid, GR_THREADS, smem, st>>>(P);
+  WWB_CHECK_LAUNCH(ctx);
+  return WWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 (layer 2, fused) - GRU-2 input projection + recurrence in one kernel.  Layer 1 leaves its output sequence in HBM
+// as a packed fp16 hi/lo operand (32 KB per 128 windows and step); here it is the A operand of
+//     acc_dir[128, 0:96]  = seq1[t][128, 64] . W2_dir^T + b_in      columns  xh | z | r      (issued ahead of h)
+//     acc_dir[128, 32:96] += h_dir[128, 32] . U_zr^T                                  z | r
+//     acc_dir[128, 96:128] = h_dir[128, 32] . U_h^T                                   hh
+// so the 14.6 KB/window xw2 tensor is never written to or read from HBM (it was 3.2 GB each way per bench step) and the
+// separate projection GEMM kernel is gone.  z and r leave the tensor core already summed (x part + h part); only the
+// candidate gate needs its two parts separately.  The slab of step s+1 streams in (cp.async.bulk) while step s runs.
+constexpr int G2_W_BYTES = 2 * 8 * 96 * 16;        // per direction: hi + lo planes, K = 64, N = 96
+constexpr int G2_BIAS_BYTES = 2 * 96 * 16;         // B operand of the 'ones' k-step
+constexpr int G2_AST = 2;                          // A slab stages per direction
+
+struct G2Smem {
+  unsigned char a[2][G2_AST][G2_A_BYTES];
+  unsigned char w[2][G2_W_BYTES];
+  unsigned char u[2][GR_U_BYTES];
+  unsigned char bias_B[2][G2_BIAS_BYTES];
+  float bh[2][32];
+  uint64_t acc_full[2], acc_free[2], h_ready[2];
+  uint64_t a_full[2][G2_AST], a_empty[2][G2_AST];
+  uint32_t tmem_base;
+};
+
+struct G2Params {
+  const unsigned char* seq;     // packed layer-1 output (GrParams::seq_packed)
+  const unsigned char* w2;      // [2][G2_W_BYTES]
+  const unsigned char* u;       // [2][GR_U_BYTES]
+  const float* b_in;            // [2][96] in accumulator column order xh | z | r
+  const float* bh;              // [2][32]
+  float* last_out;              // [B, 64]
+  int64_t n_win;
+  const int32_t* n_win_dev;
+  int nsplit;
+};
+
+__global__ void __launch_bounds__(GR_THREADS, 1) gru2_fused_tc_kernel(const G2Params P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  G2Smem& sm = *reinterpret_cast<G2Smem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int64_t n_win = P.n_win_dev ? (int64_t)*P.n_win_dev : P.n_win;
+  const int64_t n_tiles = (n_win + 127) / 128;
+
+  for (int i = tid; i < (int)(2 * G2_W_BYTES / 16); i += GR_THREADS)
+    reinterpret_cast<uint4*>(&sm.w[0][0])[i] = reinterpret_cast<const uint4*>(P.w2)[i];
+  for (int i = tid; i < (int)(2 * GR_U_BYTES / 16); i += GR_THREADS)
+    reinterpret_cast<uint4*>(&sm.u[0][0])[i] = reinterpret_cast<const uint4*>(P.u)[i];
+  for (int i = tid; i < (int)(2 * G2_BIAS_BYTES / 16); i += GR_THREADS) reinterpret_cast<uint4*>(&sm.bias_B[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 64) (&sm.bh[0][0])[tid] = P.bh[tid];
+  __syncthreads();
+  if (tid < 192) {   // row n of direction d = (hi, lo, 0, ...); the second chunk stays 0
+    __half bhi, blo;
+    split_f16(P.b_in[tid], bhi, blo);
+    reinterpret_cast<uint32_t*>(&sm.bias_B[tid / 96][(tid % 96) * 16])[0] = pack_h2(bhi, blo);
+  }
+  if (tid == 0) {
+    for (int d = 0; d < 2; ++d) {
+      mbar_init(&sm.acc_full[d], 1); mbar_init(&sm.acc_free[d], 4); mbar_init(&sm.h_ready[d], 4);
+      for (int i = 0; i < G2_AST; ++i) { mbar_init(&sm.a_full[d][i], 1); mbar_init(&sm.a_empty[d][i], 1); }
+    }
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(&sm.tmem_base, 512);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t TM_H = 256, TM_ONE = 320;   // accumulators: direction d at columns d*128; h operand: 256 + d*32; constant chunk (1, 1, 0, ...)
+  if (warp < 4) {
+    uint32_t one[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) one[i] = 0u;
+    one[0] = 0x3c003c00u;
+    tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + TM_ONE, one);
+    tmem_st_wait();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+
+  if (warp < 8) {
+    const int d = warp >> 2, q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + d * 128;
+    const uint32_t th = tmem + ((uint32_t)(q * 32) << 16) + TM_H + d * 32;
+    const float* bh = sm.bh[d];
+    uint32_t n_acc = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t b = tile * 128 + r;
+      const bool valid = b < n_win;
+      float h[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) h[i] = 0.f;
+      for (int s = 0; s < GR_T; ++s, ++n_acc) {
+        mbar_wait(&sm.acc_full[d], n_acc & 1);
+        fence_after_sync();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float xh[8], az[8], ar[8], hh[8];
+          tmem_ld8f(tbase + u * 8, xh);
+          tmem_ld8f(tbase + 32 + u * 8, az);
+          tmem_ld8f(tbase + 64 + u * 8, ar);
+          if (s > 0) {
+            tmem_ld8f(tbase + 96 + u * 8, hh);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hh[i] = 0.f;
+          }
+          tmem_ld_wait();
+          if (u == 3) {   // the accumulator has been read: the next step's input projection may overwrite it
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.acc_free[d]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float z = sigmoid_fast(az[i]);
+            const float rr = sigmoid_fast(ar[i]);
+            const float c = tanh_fast(fmaf(rr, hh[i] + bh[u * 8 + i], xh[i]));
+            h[u * 8 + i] = fmaf(z, h[u * 8 + i] - c, c);
+          }
+        }
+        if (s < GR_T - 1) {
+          uint32_t hr16[16], lr16[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) split_pair(h[2 * c], h[2 * c + 1], hr16[c], lr16[c]);
+          fence_before_sync();
+          tmem_st16(th, hr16);
+          tmem_st16(th + 16, lr16);
+          tmem_st_wait();
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.h_ready[d]);
+        }
+      }
+      if (valid) {
+        float4* dst = reinterpret_cast<float4*>(P.last_out + b * 64 + d * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+      }
+    }
+  } else {
+    // MMA issuer + slab loader
+    const uint32_t idesc_x = make_idesc_f16(128, 96), idesc_zr = make_idesc_f16(128, 64), idesc_h = make_idesc_f16(128, 32);
+    const int nsplit = P.nsplit;
+    uint32_t n_ld[2] = {0, 0};
+    int64_t ld_tile[2] = {blockIdx.x, blockIdx.x};
+    int ld_s[2] = {0, 0};
+    auto load_next = [&](const int dd) {   // requests direction dd's next slab if its stage is free (never blocks)
+      if (ld_tile[dd] >= n_tiles) return;
+      const int xs = n_ld[dd] % G2_AST;
+      if (n_ld[dd] >= (uint32_t)G2_AST) {
+        uint32_t ok = 0;
+        if (lane == 0) ok = mbar_test_wait(&sm.a_empty[dd][xs], ((n_ld[dd] / G2_AST) & 1) ^ 1) ? 1u : 0u;
+        if (!__shfl_sync(0xffffffffu, ok, 0)) return;
+      }
+      const int t = dd ? GR_T - 1 - ld_s[dd] : ld_s[dd];
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&sm.a_full[dd][xs], G2_A_BYTES);
+        bulk_g2s(sm.a[dd][xs], P.seq + (size_t)(ld_tile[dd] * GR_T + t) * G2_A_BYTES, G2_A_BYTES, &sm.a_full[dd][xs]);
+      }
+      ++n_ld[dd];
+      if (++ld_s[dd] == GR_T) { ld_s[dd] = 0; ld_tile[dd] += gridDim.x; }
+    };
+    load_next(0); load_next(1); load_next(0); load_next(1);
+    uint32_t n_step = 0, n_h = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int s = 0; s < GR_T; ++s, ++n_step) {
+        // input projections of this step (do not depend on h): as soon as the slab is in and the accumulator has been read
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          load_next(0);
+          load_next(1);
+          const int xs = n_step % G2_AST;
+          mbar_wait(&sm.a_full[d][xs], (n_step / G2_AST) & 1);
+          if (n_step > 0) mbar_wait(&sm.acc_free[d], (n_step - 1) & 1);
+          fence_after_sync();
+          if (elect_one()) {
+            const uint32_t acc = tmem + d * 128;
+            const uint64_t da = make_desc(smem_u32(sm.a[d][xs]), 2048, 128), db = make_desc(smem_u32(sm.w[d]), 1536, 128);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t dah = da + (uint64_t)((kk * 4096) >> 4), dal = dah + (uint64_t)((G2_A_BYTES / 2) >> 4);
+              const uint64_t dbh = db + (uint64_t)((kk * 3072) >> 4), dbl = dbh + (uint64_t)((G2_W_BYTES / 2) >> 4);
+              mma_f16_ss(acc, dah, dbh, idesc_x, kk != 0);
+              if (nsplit == 3) {
+                mma_f16_ss(acc, dal, dbh, idesc_x, true);
+                mma_f16_ss(acc, dah, dbl, idesc_x, true);
+              }
+            }
+            mma_f16_ts(acc, tmem + TM_ONE, make_desc(smem_u32(sm.bias_B[d]), 1536, 128), idesc_x, true);   // + b_in
+            mma_commit(&sm.a_empty[d][xs]);
+            if (s == 0) mma_commit(&sm.acc_full[d]);   // h = 0: no recurrent part
+          }
+          __syncwarp();
+        }
+        if (s == 0) continue;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          load_next(0);
+          load_next(1);
+          mbar_wait(&sm.h_ready[d], n_h & 1);
+          fence_after_sync();
+          if (elect_one()) {
+            const uint32_t acc = tmem + d * 128, ta = tmem + TM_H + d * 32;
+            const uint64_t db = make_desc(smem_u32(sm.u[d]), 1536, 128);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t dbh = db + (uint64_t)((kk * 3072) >> 4), dbl = dbh + (uint64_t)((GR_U_BYTES / 2) >> 4);
+              const uint64_t hoff = (uint64_t)((64 * 16) >> 4);   // U rows 64..95: candidate gate
+              mma_f16_ts(acc + 32, ta + kk * 8, dbh, idesc_zr, true);
+              mma_f16_ts(acc + 96, ta + kk * 8, dbh + hoff, idesc_h, kk != 0);
+              if (nsplit == 3) {
+                mma_f16_ts(acc + 32, ta + 16 + kk * 8, dbh, idesc_zr, true);
+                mma_f16_ts(acc + 32, ta + kk * 8, dbl, idesc_zr, true);
+                mma_f16_ts(acc + 96, ta + 16 + kk * 8, dbh + hoff, idesc_h, true);
+                mma_f16_ts(acc + 96, ta + kk * 8, dbl + hoff, idesc_h, true);
+              }
+            }
+            mma_commit(&sm.acc_full[d]);
+          }
+          __syncwarp();
+        }
+        ++n_h;
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// W2 [192][64] (row = fwd gates z|r|h then bwd gates z|r|h) -> per direction [plane][8 chunks][96 rows xh|z|r][8 halves]
+std::vector<unsigned char> crnn_pack_w2(const float* w_nk) {
+  std::vector<unsigned char> out(2 * G2_W_BYTES, 0);
+  for (int d = 0; d < 2; ++d)
+    for (int c = 0; c < 8; ++c)
+      for (int n = 0; n < 96; ++n) {
+        const int src_row = d * 96 + (n < 32 ? 64 + n : n - 32);
+        for (int e = 0; e < 8; ++e) {
+          const size_t off = (size_t)d * G2_W_BYTES + ((size_t)c * 96 + n) * 16 + e * 2;
+          put_split16(out, off, off + G2_W_BYTES / 2, w_nk[(size_t)src_row * 64 + c * 8 + e]);
+        }
+      }
+  return out;
+}
+// input bias [2][96] (z|r|h, recurrent z/r bias folded in) -> accumulator column order xh|z|r
+std::vector<float> crnn_reorder_bias2(const float* bf) {
+  std::vector<float> out(192);
+  for (int d = 0; d < 2; ++d)
+    for (int n = 0; n < 96; ++n) out[d * 96 + n] = bf[d * 96 + (n < 32 ? 64 + n : n - 32)];
+  return out;
+}
+size_t crnn_seq_packed_bytes(int64_t B) { return (size_t)((B + 127) / 128) * GR_T * G2_A_BYTES; }
+
+int gru2_fused_tc(wwb_ctx* ctx, const unsigned char* seq_packed, float* last_out, int64_t B, const int32_t* n_dev,
+                  cudaStream_t st) {
+  if (B == 0) return WWB_OK;
+  G2Params P;
+  memset(&P, 0, sizeof(P));
+  P.seq = seq_packed;
+  P.w2 = ctx->crnn.tc_w2;
+  P.u = ctx->crnn.tc_u[1];
+  P.b_in = ctx->crnn.tc_bi2;
+  P.bh = ctx->crnn.tc_bh[1];
+  P.last_out = last_out;
+  P.n_win = B;
+  P.n_win_dev = n_dev;
+  P.nsplit = ctx->precision == WWB_PREC_TC ? 3 : 1;
+  const size_t smem = sizeof(G2Smem) + 128;
+  WWB_CUDA(ctx, cudaFuncSetAttribute(gru2_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n_tiles = (B + 127) / 128;
+  const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count);
+  gru2_fused_tc_kernel<<<grid, GR_THREADS, smem, st>>>(P);
   WWB_CHECK_LAUNCH(ctx);
   return WWB_OK;
 }
