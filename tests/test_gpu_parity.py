@@ -176,8 +176,8 @@ def test_tc_fast_mode_is_close_but_outside_parity(wname, name):
     assert np.abs(exact - ref).max() <= np.abs(fast - ref).max()
 
 
-def test_tc_gemm_many_tiles_matches_f32_path():
-    """8192 windows (155648 GEMM rows, > 8 tiles per SM, ragged last tile) through both paths."""
+def test_crnn_tc_many_tiles_matches_f32_path():
+    """8191 independent windows (ragged last tile of every kernel) through both paths."""
     import torch
     e32, etc = get_engine("CRNN", "f32"), get_engine("CRNN", "tc")
     pcm = synth.device_pcm(64, 160 * 300 + 512, seed=3, device=e32.device)
@@ -500,3 +500,22 @@ def test_encoders_are_deterministic(wname):
         ref = eng.posteriors(mel, 2).clone()
         for _ in range(6):
             assert torch.equal(eng.posteriors(mel, 2), ref)
+
+
+@pytest.mark.parametrize("S,F,hop", [(2, 411, 2), (5, 998, 2), (2, 700, 1), (3, 600, 4), (2, 1200, 8), (1, 153, 2), (40, 998, 2)])
+def test_crnn_shared_columns_bit_identical_to_per_window_path(S, F, hop):
+    """Sliding-window batches compute every conv / GRU-1 projection column once per stream position (crnn_tc.cu,
+    CrnnShare); WWB_CRNN_NO_SHARE=1 forces the per-window tiles.  Same MMAs on the same operands: identical bits."""
+    import os
+    import torch
+    tc, f32 = get_engine("CRNN", "tc"), get_engine("CRNN", "f32")
+    torch.manual_seed(S * 1000 + F)
+    X = torch.rand((S, F, 40), device=tc.device) * 5
+    os.environ["WWB_CRNN_NO_SHARE"] = "1"
+    try:
+        a = tc.posteriors(X, hop=hop).clone()
+    finally:
+        os.environ["WWB_CRNN_NO_SHARE"] = "0"
+    b = tc.posteriors(X, hop=hop).clone()
+    assert bool((a == b).all())
+    assert float((b - f32.posteriors(X, hop=hop)).abs().max()) < 1e-4

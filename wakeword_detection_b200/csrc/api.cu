@@ -152,7 +152,6 @@ static int build_crnn(wwb_ctx* ctx, const wwb_weights* w) {
       std::vector<float> w_nk((size_t)192 * in);
       for (int dir = 0; dir < 2; ++dir)
         memcpy(&w_nk[(size_t)dir * 96 * in], w->gru_w[layer * 2 + dir], sizeof(float) * 96 * in);
-      if ((rc = upload(ctx, pack_gemm_b(w_nk.data(), in, true), &C.gemm_b[layer]))) return rc;
       if (layer == 0 && (rc = upload(ctx, crnn_pack_w1(w_nk.data()), &C.tc_w1))) return rc;
       if (layer == 1 && (rc = upload(ctx, crnn_pack_w2(w_nk.data()), &C.tc_w2))) return rc;
     }

@@ -43,7 +43,6 @@ struct CrnnWeights {   // device copies, fp32, layouts chosen for the kernels
   float* det1_b = nullptr;
   float* det2_w = nullptr;   // [n_out][64]
   float* det2_b = nullptr;
-  unsigned char* gemm_b[2] = {};   // tensor-core path: packed hi/lo fp16 weight stages (tc_gemm.cu), per layer
   unsigned char* tc_conv = nullptr;   // crnn_tc.cu: packed conv weights
   unsigned char* tc_w1 = nullptr;     // crnn_tc.cu: 20 packed k-slices of the layer-1 input projection
   unsigned char* tc_u[2] = {};        // crnn_tc.cu: packed recurrent weights, both directions, per layer
@@ -171,9 +170,6 @@ struct WinMap {
   int ring;                   // rows per stream
 };
 
-std::vector<unsigned char> pack_gemm_b(const float* w_nk, int K, bool split);
-int tc_gemm_bias(wwb_ctx* ctx, const float* A, const unsigned char* Bpacked, const float* bias, float* C, int64_t M,
-                 int K, int nsplit, int xw_layout, cudaStream_t st);
 int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
                          float* post, cudaStream_t st);
 int crnn_simt_detect(wwb_ctx* ctx, const float* enc, int64_t B, float* out, cudaStream_t st);
@@ -186,8 +182,8 @@ struct CrnnShare {
 };
 bool crnn_share_plan(const WinMap& wm, int L, CrnnShare* out);
 size_t crnn_share_xws_bytes(const CrnnShare& g, int64_t n_streams);
-size_t crnn_share_xwb_bytes(const CrnnShare& g, int64_t n_streams);
-int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st, int mode = 0, const CrnnShare* g = nullptr);
+int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st, int mode = 0, const CrnnShare* g = nullptr,
+                  int variant = 0);
 std::vector<unsigned char> crnn_pack_u(const float* u_f, const float* u_b);
 int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* last_out, int64_t B,
                const int32_t* n_dev, cudaStream_t st, const float* xws = nullptr, const CrnnShare* g = nullptr,

@@ -235,10 +235,8 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
   int rc;
   // the 48.6 KB/window conv intermediate exists only on the fp32 validation path (1.8 GB per chunk)
   if (ctx->precision == WWB_PREC_F32 && (rc = workspace(ctx, 1, (size_t)std::min(B, chunk) * C_T * C_FEAT * 4, &conv))) return rc;
-  if (shared && (rc = workspace(ctx, 1, crnn_share_xws_bytes(sh, chunk_streams), &xws))) return rc;
-  size_t xw_bytes = (size_t)((std::min(B, chunk) + 127) / 128 * 128) * C_T * 2 * C_G * 4;
-  if (shared) xw_bytes = std::max(xw_bytes, crnn_share_xwb_bytes(sh, chunk_streams));
-  if ((rc = workspace(ctx, 2, xw_bytes, &xw))) return rc;
+  if (shared && (rc = workspace(ctx, 1, 3 * crnn_share_xws_bytes(sh, chunk_streams), &xws))) return rc;
+  if ((rc = workspace(ctx, 2, shared ? 16 : (size_t)((std::min(B, chunk) + 127) / 128 * 128) * C_T * 2 * C_G * 4, &xw))) return rc;
   // layer-1 output: fp32 [B, 19, 64] (fp32 path) or the packed fp16 hi/lo operand of the fused layer-2 kernel (same bytes per value)
   if ((rc = workspace(ctx, 3, std::max((size_t)std::min(B, chunk) * C_T * 64 * 4, crnn_seq_packed_bytes(std::min(B, chunk))), &s1))) return rc;
   if ((rc = workspace(ctx, 4, (size_t)std::min(B, chunk) * 64 * 4, &enc_ws))) return rc;
@@ -256,10 +254,11 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
     const int64_t M = nb * C_T;
     // both directions of a layer share one GEMM: Wt = [in][192]
     const bool tc = ctx->precision != WWB_PREC_F32;
-    const int nsplit = ctx->precision == WWB_PREC_TC ? 3 : 1;
     if (shared) {
-      if ((rc = crnn_front_tc(ctx, sub, (float*)xws, st, 1, &sh))) return rc;   // interior columns, once per position
-      if ((rc = crnn_front_tc(ctx, sub, (float*)xw, st, 2, &sh))) return rc;    // padded columns t = 0 / 18 per window
+      // interior columns once per position, then the padded columns t = 0 / 18 (same strips, masked conv weights)
+      const size_t vbytes = crnn_share_xws_bytes(sh, nb / sh.wps);
+      for (int v = 0; v < 3; ++v)
+        if ((rc = crnn_front_tc(ctx, sub, (float*)((unsigned char*)xws + v * vbytes), st, 1, &sh, v))) return rc;
     } else if (tc) {
       if ((rc = crnn_front_tc(ctx, sub, (float*)xw, st))) return rc;
     } else {
@@ -269,15 +268,10 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
                                                                             (float*)xw, M, 2 * C_G, C_FEAT);
       WWB_CHECK_LAUNCH(ctx);
     }
-    const char* no_fuse = getenv("WWB_CRNN_NO_FUSE2");
-    if (tc && !(no_fuse && no_fuse[0] == '1')) {
+    if (tc) {
       // layer 1 leaves its output as the packed A operand of layer 2's input projection, which the layer-2 kernel computes itself
       if ((rc = gru_rec_tc(ctx, 0, (float*)xw, nullptr, nullptr, nb, wm.n_win_dev, st, (float*)xws, &sh, (unsigned char*)s1))) return rc;
       if ((rc = gru2_fused_tc(ctx, (unsigned char*)s1, enc, nb, wm.n_win_dev, st))) return rc;
-    } else if (tc) {
-      if ((rc = gru_rec_tc(ctx, 0, (float*)xw, (float*)s1, nullptr, nb, wm.n_win_dev, st, (float*)xws, &sh))) return rc;
-      if ((rc = tc_gemm_bias(ctx, (float*)s1, W.gemm_b[1], W.tc_bi[1], (float*)xw, M, 64, nsplit, 1, st))) return rc;
-      if ((rc = gru_rec_tc(ctx, 1, (float*)xw, nullptr, enc, nb, wm.n_win_dev, st))) return rc;
     } else {
       gru_rec_kernel<<<(unsigned)((nb + 3) / 4), 256, 0, st>>>((float*)xw, W.gru_u[0], W.gru_br[0], W.gru_u[1],
                                                               W.gru_br[1], (float*)s1, nullptr, nb, wm.n_win_dev);

@@ -65,16 +65,15 @@ struct CaSmem {
 // is 8 frames, so column t of window j covers frames h*j + 8t - 6 .. + 13 and depends only on the POSITION INDEX
 // m = j + q*t (q = 8/h) as long as it does not touch the window's zero padding, i.e. for t = 1..17.  Those columns (and
 // their 192-wide GRU-1 input projection) are computed once per stream and position by tiles that are STRIPS of 126
-// consecutive conv steps of one stream and phase (mode 1); the two padded columns t = 0 / 18 of every window are
-// computed by tiles of 25 windows with 5 elements each (mode 2): [A0 A1 A2 B0 B1], A = frames -6..17 (column t = 0,
-// row slot 0), B = frames 138..153 (column t = 18, row slot 3).  Column 18's third chunk (frames 154..161, all padding)
-// is whatever element follows - the next window's A0, whose first six values are zero padding and whose last two meet
-// the zero weights of the (non-existent) time taps 22 and 23: it contributes exactly 0.  Each column is the same MMA sequence on the same
-// operands as in mode 0, so the results are bit-identical.
-//   xwS: [stream][48 float4 columns][Mp positions]            (interior columns, mode 1)
-//   xwB: [recurrence tile = stream*tps + j/128][2][48][128]   (t = 0 and t = 18, mode 2)
-enum { CA_MODE_WINDOWS = 0, CA_MODE_STRIPS = 1, CA_MODE_BOUNDARY = 2 };
-constexpr int CA_STRIP_ROWS = 126, CA_BWIN = 25, CA_BSLOTS = 5;
+// consecutive conv steps of one stream and phase (mode 1).  The two padded columns of a window are strips as well, with
+// the padding moved from the data into the WEIGHTS: column t = 0 of window j is the conv at position m = j with the time
+// taps 0..5 zeroed (they would meet the 6 padding frames), column t = 18 the conv at m = j + 18q with taps 13..19 zeroed.
+// Each column is the same MMA sequence as in mode 0 with zero products in the same places, so the results are
+// bit-identical.  One launch per weight variant writes its own buffer
+//   xwS[variant][stream][48 float4 columns][Mp positions]     variant 0: interior, 1: t = 0, 2: t = 18
+// and the layer-1 recurrence reads 128 consecutive positions m = j0 + q*t .. of the variant that step t needs.
+enum { CA_MODE_WINDOWS = 0, CA_MODE_STRIPS = 1 };
+constexpr int CA_STRIP_ROWS = 126;
 // geometry: CrnnShare (common.cuh): q = position indices per conv step (8 / hop), nsp = strips per stream and phase,
 // Mp = positions per xwS column row (q * 126 * nsp), F = frames of a stream covered by windows, wps = windows per
 // stream, tps = recurrence tiles per stream
@@ -195,7 +194,7 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         const int64_t w = tile * CA_WPT + wl;
         valid = (wl < CA_WPT) && (t < CA_T) && (w < n_win);
         b = (((w >> 7) * CA_T + t) * 48) * 128 + (w & 127);
-      } else if (mode == CA_MODE_STRIPS) {
+      } else {
         const int per = P.sh.q * P.sh.nsp;
         const int64_t stream = tile / per;
         const int rem = (int)(tile - stream * per);
@@ -203,13 +202,6 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         const int m = phase + P.sh.q * (CA_STRIP_ROWS * k + r);
         valid = r < CA_STRIP_ROWS;
         b = stream * 48 * P.sh.Mp + m;
-      } else {
-        const int wl2 = r / CA_BSLOTS, slot = r - wl2 * CA_BSLOTS;
-        const int64_t w = tile * CA_BWIN + wl2;
-        valid = (slot == 0 || slot == 3) && wl2 < CA_BWIN && w < n_win;
-        const int64_t stream = w / P.sh.wps;
-        const int j = (int)(w - stream * P.sh.wps);
-        b = (((stream * P.sh.tps + (j >> 7)) * 2 + (slot == 3)) * 48) * 128 + (j & 127);
       }
       for (int f = 0; f < CA_F; ++f) {
         const uint32_t ci = tcount * CA_F + f;
@@ -410,7 +402,7 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         if (live) win_origin(P.wm, b, s, start);
         f0 = 8 * c - 6;
         fhi = P.L;
-      } else if (mode == CA_MODE_STRIPS) {
+      } else {
         const int per = P.sh.q * P.sh.nsp;
         s = tile / per;
         const int rem = (int)(tile - s * per);
@@ -418,13 +410,6 @@ __global__ void __launch_bounds__(CA_THREADS, 1) crnn_front_tc_kernel(const CaPa
         live = true;
         f0 = (8 / P.sh.q) * phase + 8 * (CA_STRIP_ROWS * k + task) - 6;
         fhi = P.sh.F;
-      } else {
-        const int wl2 = task / CA_BSLOTS, c = task - wl2 * CA_BSLOTS;   // chunks 0..2: column t = 0, chunks 3..4: column t = 18
-        const int64_t b = tile * CA_BWIN + wl2;
-        live = wl2 < CA_BWIN && b < n_win;
-        if (live) win_origin(P.wm, b, s, start);
-        f0 = (c < 3 ? 8 * c : 8 * (CA_T - 1) + 8 * (c - 3)) - 6;
-        fhi = P.L;
       }
       for (int g = 0; g < CA_GROUPS; ++g, ++gg) {
         if ((int)(gg & 1) != pset) continue;
@@ -484,17 +469,20 @@ static void put_split16(std::vector<unsigned char>& buf, size_t hi_off, size_t l
   memcpy(&buf[lo_off], &l, 2);
 }
 
-// conv_w [32][5][20] -> [plane][16 chunks][32 channels][8 halves]; chunk q = kf*3 + j holds time taps 8j..8j+7
+// conv_w [32][5][20] -> 3 variants x [plane][16 chunks][32 channels][8 halves]; chunk q = kf*3 + j holds time taps 8j..8j+7.
+// Variant 0: all taps; 1: taps 0..5 zeroed (column t = 0 of a window: its first 6 frames are padding); 2: taps 13..19
+// zeroed (column t = 18: frames 151.. are padding)
 std::vector<unsigned char> crnn_pack_conv(const float* conv_w) {
-  std::vector<unsigned char> out(2 * CA_CW_PLANE, 0);
-  for (int q = 0; q < 15; ++q)
-    for (int n = 0; n < 32; ++n)
-      for (int e = 0; e < 8; ++e) {
-        const int kf = q / 3, kt = (q % 3) * 8 + e;
-        if (kt >= 20) continue;
-        const size_t off = ((size_t)q * 32 + n) * 16 + e * 2;
-        put_split16(out, off, off + CA_CW_PLANE, conv_w[(n * 5 + kf) * 20 + kt]);
-      }
+  std::vector<unsigned char> out((size_t)3 * 2 * CA_CW_PLANE, 0);
+  for (int v = 0; v < 3; ++v)
+    for (int q = 0; q < 15; ++q)
+      for (int n = 0; n < 32; ++n)
+        for (int e = 0; e < 8; ++e) {
+          const int kf = q / 3, kt = (q % 3) * 8 + e;
+          if (kt >= 20 || (v == 1 && kt < 6) || (v == 2 && kt >= 13)) continue;
+          const size_t off = (size_t)v * 2 * CA_CW_PLANE + ((size_t)q * 32 + n) * 16 + e * 2;
+          put_split16(out, off, off + CA_CW_PLANE, conv_w[(n * 5 + kf) * 20 + kt]);
+        }
   return out;
 }
 
@@ -529,15 +517,15 @@ bool crnn_share_plan(const WinMap& wm, int L, CrnnShare* out) {
   g.Mp = g.q * CA_STRIP_ROWS * g.nsp;
   g.n_streams = wm.n_win / wps;
   // worth it only if it is fewer tiles than 6 windows per tile
-  const int64_t tiles_shared = g.n_streams * g.q * g.nsp + (wm.n_win + CA_BWIN - 1) / CA_BWIN;
+  const int64_t tiles_shared = 3 * g.n_streams * g.q * g.nsp;
   if (tiles_shared >= (wm.n_win + CA_WPT - 1) / CA_WPT) return false;
   *out = g;
   return true;
 }
+// one variant's buffer (+ slack: the recurrence reads 128 positions from j0 + q*t even where fewer windows are left)
 size_t crnn_share_xws_bytes(const CrnnShare& g, int64_t n_streams) { return ((size_t)n_streams * 48 * g.Mp + 256) * 16; }
-size_t crnn_share_xwb_bytes(const CrnnShare& g, int64_t n_streams) { return (size_t)n_streams * g.tps * 2 * 48 * 128 * 16; }
 
-int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st, int mode, const CrnnShare* g) {
+int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st, int mode, const CrnnShare* g, int variant) {
   if (wm.n_win == 0) return WWB_OK;
   CaParams P;
   memset(&P, 0, sizeof(P));
@@ -545,11 +533,11 @@ int crnn_front_tc(wwb_ctx* ctx, const WinMap& wm, float* xw1, cudaStream_t st, i
   int64_t n_tiles = (wm.n_win + CA_WPT - 1) / CA_WPT;
   if (mode != CA_MODE_WINDOWS) {
     P.sh = *g;
-    n_tiles = mode == CA_MODE_STRIPS ? (wm.n_win / g->wps) * g->q * g->nsp : (wm.n_win + CA_BWIN - 1) / CA_BWIN;
+    n_tiles = (wm.n_win / g->wps) * g->q * g->nsp;
   }
   P.n_tiles = n_tiles;
   P.wm = wm;
-  P.cw = ctx->crnn.tc_conv;
+  P.cw = ctx->crnn.tc_conv + (size_t)variant * 2 * CA_CW_PLANE;
   P.w1 = ctx->crnn.tc_w1;
   P.conv_b = ctx->crnn.conv_b;
   P.b_in = ctx->crnn.tc_bi[0];
@@ -602,8 +590,9 @@ struct GrSmem {
 };
 
 struct GrParams {
-  const float* xw;              // [ceil(B/128), 19, 48, 128] float4 (shared-column mode: xwB, [tile][2][48][128])
-  const float* xws;             // shared-column mode: interior columns [stream][48][Mp] float4, else null
+  const float* xw;              // [ceil(B/128), 19, 48, 128] float4
+  const float* xws;             // shared-column mode (else null): [3 variants][stream][48][Mp] float4 by position (CrnnShare)
+  size_t xws_variant;           // bytes between two variants
   int q, Mp, wps, tps;          // shared-column geometry (CaShare); tiles are then per stream: tile = stream*tps + j/128
   int64_t n_tiles;
   const unsigned char* u;       // [2][GR_U_BYTES] packed
@@ -785,18 +774,18 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
       const int t = dd ? GR_T - 1 - ld_s[dd] : ld_s[dd];
       if (lane == 0) mbar_arrive_expect_tx(&sm.x_full[dd][xs], GR_X_BYTES);
       __syncwarp();
-      if (shared && t != 0 && t != GR_T - 1) {
-        // interior column: 128 consecutive positions (windows j0.. at step t sit at m = j0 + q*t ..) of 24 column rows
+      if (shared) {
+        // 128 consecutive positions (windows j0.. at step t sit at m = j0 + q*t ..) of 24 column rows; the padded
+        // columns t = 0 / 18 come from their own variants of the strip computation
         const int64_t stream = ld_tile[dd] / P.tps;
         const int j0 = (int)(ld_tile[dd] - stream * P.tps) * 128;
+        const unsigned char* base = reinterpret_cast<const unsigned char*>(P.xws) + (t == 0 ? 1 : t == GR_T - 1 ? 2 : 0) * P.xws_variant;
         if (lane < 24)
-          bulk_g2s(sm.x[dd][xs] + lane * 2048,
-                   reinterpret_cast<const unsigned char*>(P.xws) + (((size_t)stream * 48 + dd * 24 + lane) * P.Mp + j0 + P.q * t) * 16,
-                   2048, &sm.x_full[dd][xs]);
+          bulk_g2s(sm.x[dd][xs] + lane * 2048, base + (((size_t)stream * 48 + dd * 24 + lane) * P.Mp + j0 + P.q * t) * 16, 2048,
+                   &sm.x_full[dd][xs]);
       } else if (lane == 0) {
-        const size_t slab = shared ? (size_t)ld_tile[dd] * 2 + (t != 0) : (size_t)ld_tile[dd] * GR_T + t;
-        bulk_g2s(sm.x[dd][xs], reinterpret_cast<const unsigned char*>(P.xw) + (slab * 48 + dd * 24) * 128 * 16, GR_X_BYTES,
-                 &sm.x_full[dd][xs]);
+        bulk_g2s(sm.x[dd][xs], reinterpret_cast<const unsigned char*>(P.xw) + ((size_t)(ld_tile[dd] * GR_T + t) * 48 + dd * 24) * 128 * 16,
+                 GR_X_BYTES, &sm.x_full[dd][xs]);
       }
       ++n_ld[dd];
       if (++ld_s[dd] == GR_T) { ld_s[dd] = 0; ld_tile[dd] += gridDim.x; }
@@ -860,6 +849,7 @@ int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* 
   if (xws) {
     P.xws = xws;
     P.q = g->q; P.Mp = g->Mp; P.wps = g->wps; P.tps = g->tps;
+    P.xws_variant = crnn_share_xws_bytes(*g, B / g->wps);
     n_tiles = (B / g->wps) * g->tps;
   }
   P.n_tiles = n_tiles;
