@@ -322,21 +322,37 @@ def main():
 
     # End to end: the streams are pushed through in E2E_CHUNKS slices; the host->device copy of slice i+1 (copy stream)
     # overlaps filter -> encode -> detect of slice i (compute stream), as a caller feeding host buffers would do it.
-    E2E_CHUNKS = 4 if S % 4 == 0 and S >= 8 else 1
+    # The first slice is small (its copy is the only one nothing can hide); slice sizes are multiples of the engines'
+    # stream granule (whole waves of the persistent kernels).
+    gran = max([e.stream_granule(F, 2) for e in engines.values()] or [1])
+    if S >= 64:
+        units = max(1, S // gran) if gran * 4 <= S else 0
+        if units:
+            per = max(1, (units - 1) // 3)
+            bounds = [0, gran, gran * (1 + per), gran * (1 + 2 * per), S]
+        else:
+            first_n = max(1, S // 16)
+            rest = S - first_n
+            bounds = [0, first_n, first_n + rest // 3, first_n + 2 * (rest // 3), S]
+    else:
+        bounds = [0, S]
+    if os.environ.get("WWB_E2E_BOUNDS"):
+        bounds = [int(x) for x in os.environ["WWB_E2E_BOUNDS"].split(",")]
+    E2E_CHUNKS = len(bounds) - 1
     copy_stream = torch.cuda.Stream(device=dev)
     copied = [torch.cuda.Event() for _ in range(E2E_CHUNKS)]
 
     def e2e_step():
-        cs = S // E2E_CHUNKS
         main = torch.cuda.current_stream(dev)
         copy_stream.wait_stream(main)          # the staging buffer of the previous step is free
         with torch.cuda.stream(copy_stream):
             for i in range(E2E_CHUNKS):
-                pcm_stage[i * cs:(i + 1) * cs].copy_(pcm_host[i * cs:(i + 1) * cs], non_blocking=True)
+                sl = slice(bounds[i], bounds[i + 1])
+                pcm_stage[sl].copy_(pcm_host[sl], non_blocking=True)
                 copied[i].record(copy_stream)
         for i in range(E2E_CHUNKS):
             main.wait_event(copied[i])
-            sl = slice(i * cs, (i + 1) * cs)
+            sl = slice(bounds[i], bounds[i + 1])
             first.filter(pcm_stage[sl], 0.0, out=mel[sl])
             for m in models:
                 engines[m].posteriors(mel[sl], 2, out=post[m][sl])

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "wwb_sync": (C.c_int, [_vp, _vp]),
     "wwb_num_frames": (_i64, [_i64]),
     "wwb_num_windows": (_i64, [_vp, _i64, C.c_int]),
+    "wwb_stream_granule": (_i64, [_vp, _i64, C.c_int]),
     "wwb_filter": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, C.c_float, _vp, _vp]),
     "wwb_mel_from_magnitude": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "wwb_encode": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
@@ -221,6 +222,10 @@ class Engine:
 
     def num_windows(self, n_frames: int, hop: int) -> int:
         return int(self.lib.wwb_num_windows(self.ctx, int(n_frames), int(hop)))
+
+    def stream_granule(self, n_frames: int, hop: int) -> int:
+        """Stream-count granule for callers that slice a batch (whole waves of the persistent kernels)."""
+        return int(self.lib.wwb_stream_granule(self.ctx, int(n_frames), int(hop)))
 
     # -- hot path -------------------------------------------------------------------
     def _pcm(self, pcm):

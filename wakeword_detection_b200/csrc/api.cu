@@ -337,6 +337,14 @@ int64_t wwb_num_windows(const wwb_ctx* ctx, int64_t n_frames, int hop) {
   return n_frames < ctx->L ? 0 : (n_frames - ctx->L) / hop + 1;
 }
 
+int64_t wwb_stream_granule(const wwb_ctx* ctx, int64_t n_frames, int hop) {
+  if (!ctx || ctx->kind != WWB_MODEL_CRNN || ctx->precision == WWB_PREC_F32) return 1;
+  const int64_t wps = wwb_num_windows(ctx, n_frames, hop);
+  if (wps < 1) return 1;
+  const int64_t tps = (wps + 127) / 128;   // layer-1 recurrence tiles per stream (crnn_tc.cu, CrnnShare)
+  return ctx->sm_count % tps == 0 ? ctx->sm_count / tps : 1;
+}
+
 int wwb_filter(wwb_ctx* ctx, const void* pcm, int dtype, int64_t S, int64_t N, int64_t pitch, float a, float* mel,
                void* stream) {
   if (!ctx) return WWB_ERR_ARG;
