@@ -519,3 +519,30 @@ def test_crnn_shared_columns_bit_identical_to_per_window_path(S, F, hop):
     b = tc.posteriors(X, hop=hop).clone()
     assert bool((a == b).all())
     assert float((b - f32.posteriors(X, hop=hop)).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("wname,name", [("CRNN", "crnn"), ("Wavenet", "wavenet")])
+def test_tf_lite_opts_models_predict_dropin(wname, name):
+    """utils/evaluate_tf_lite_opts.py:49-67: clips -> posterior -> non-strict `>= threshold`, here as one batch."""
+    import os
+    from conftest import WEIGHTS
+    from wakeword_detection_b200 import evaluate_tf_lite_opts as ETO
+    w = load_weights(wname)
+    X = _windows(name, w)
+    ref = R.posterior(X, w)
+    enc, det = ETO.load_tf_models(os.path.join(WEIGHTS, wname))
+    post = ETO.posteriors(enc, det, X, wname)
+    assert post.shape == (X.shape[0],) and np.abs(post - ref).max() < POST_ATOL
+    for thr in (0.5, 0.9):
+        preds = ETO.models_predict(enc, det, X, wname, threshold=thr)
+        want = [1 if p >= thr else 0 for p in ref]
+        flips = [i for i, (a, b) in enumerate(zip(preds, want)) if a != b]
+        assert all(abs(ref[i] - thr) < POST_ATOL for i in flips)       # only inside the tolerance band
+        assert 0 < sum(preds) < len(preds)
+    assert ETO.models_predict(enc, det, X, wname, threshold=float(post[0]))[0] == 1     # `>=`, not `>`
+    with pytest.raises(ValueError):
+        ETO.models_predict(enc, det, X[:, :-1], wname)
+    with pytest.raises(ValueError):
+        ETO.models_predict(enc, det, X.astype(np.float64), wname)
+    with pytest.raises(ValueError):
+        ETO.models_predict(enc, det, X, "Wavenet" if wname == "CRNN" else "CRNN")

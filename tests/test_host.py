@@ -162,3 +162,26 @@ def test_parse_args_flags():
     a = EM.parse_args(["--model_type", "Wavenet", "--models_dir", os.path.join(ROOT, "weights", "Wavenet")])
     assert a.model_type == "Wavenet" and a.sample_rate == 16000 and a.frame_width == 20
     assert a.neg_samples == "not_hey_snips_long.wav" and a.examine_audio is False
+
+
+def test_tf_lite_opts_load_data_npz_and_metrics(tmp_path, capsys):
+    """evaluate_tf_lite_opts.py:35-47 (truncate / zero-pad to `timesteps`, file order, uint8 labels) and :69-87
+    (metric definitions, including the reference's swapped recall / precision names)."""
+    from wakeword_detection_b200 import evaluate_tf_lite_opts as ETO
+    rng = np.random.default_rng(0)
+    clips = {"b_long": rng.random((200, 40), dtype=np.float32), "a_short": rng.random((37, 40), dtype=np.float32),
+             "c_exact": rng.random((151, 40), dtype=np.float32)}
+    labels = {"b_long": 1, "a_short": 0, "c_exact": 1}
+    path = str(tmp_path / "test.npz")
+    ETO.save_npz(path, clips, labels)
+    X, y = ETO.load_data(path, 151, 40)
+    assert X.shape == (3, 151, 40) and X.dtype == np.float32 and y.dtype == np.uint8
+    assert list(y) == [1, 0, 1]                                   # keys in file order, not sorted
+    assert np.array_equal(X[0], clips["b_long"][:151])
+    assert np.array_equal(X[1, :37], clips["a_short"]) and not X[1, 37:].any()
+    assert np.array_equal(X[2], clips["c_exact"])
+    r = ETO.metrics([1, 0, 1, 1, 0, 0], [1, 0, 0, 1, 1, 0])
+    assert (r["true_positive"], r["false_positive"], r["false_negative"], r["true_negative"]) == (2, 1, 1, 2)
+    assert r["recall"] == 2 / 3 and r["precision"] == 2 / 3 and abs(r["accuracy"] - 2 / 3) < 1e-12
+    a = ETO.parse_args([])
+    assert (a.tf_models_dir, a.testset, a.timesteps, a.num_features, a.model_type) == ("CRNN_tf_model", "test.h5", 151, 40, "CRNN")
