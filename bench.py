@@ -421,6 +421,16 @@ def main():
         extra[m + "_TFLOPs"] = tf
         extra[m + "_frac_of_tensor"] = tf / pk["bf16_tflops_sustained"]
         extra[m + "_windows_per_step"] = S * nwin[m]
+    if "CRNN" in models and args.precision != "f32" and nwin["CRNN"] > 72:
+        # Sliding windows share the conv + GRU-1 projection columns (crnn_tc.cu, CrnnShare): the figures above use the
+        # ALGORITHMIC flops of the per-window formulation; these are the flops the kernels execute.
+        q = 4                                                     # hop 2: position indices per conv step
+        nsp = -(-((nwin["CRNN"] - 1 + 17 * q) // q + 1) // 126)   # strips of 126 conv steps per stream and phase
+        cols = 3 * q * nsp * 126                                  # interior + two padded-column variants
+        exe = cols * (2432000 + 4669440) / 19.0 / nwin["CRNN"] + 2 * 233472 + 466944 + 8320
+        extra["CRNN_shared_columns"] = {"executed_flop_per_window": exe,
+                                        "executed_TFLOPs": S * nwin["CRNN"] * exe / (per["CRNN"] / 1e3) / 1e12,
+                                        "columns_per_window": cols / nwin["CRNN"]}
 
     if rank == 0:
         cpu = None

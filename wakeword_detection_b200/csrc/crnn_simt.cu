@@ -160,49 +160,57 @@ __global__ void __launch_bounds__(128) crnn_detect_kernel(const float* __restric
   __shared__ float hs[4][64];
   for (int i = threadIdx.x; i < 64 * 64; i += 128) (&w1s[0][0])[i] = w1t[i];
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-  const int64_t b = (int64_t)blockIdx.x * 4 + wl;
   const int64_t nB = n_dev ? (int64_t)*n_dev : B;
-  const bool live = b < nB;
-  es[wl][lane] = live ? enc[b * 64 + lane] : 0.f;
-  es[wl][lane + 32] = live ? enc[b * 64 + 32 + lane] : 0.f;
   __syncthreads();
-  float a0 = b1[lane], a1 = b1[lane + 32];
+  // one window per warp and iteration; the block keeps the 16 KB of W1 in shared memory for all its windows (with one
+  // block per 4 windows, re-staging W1 was 0.9 GB of L2 traffic per bench step and most of the kernel's time)
+  for (int64_t b = (int64_t)blockIdx.x * 4 + wl; b < nB; b += (int64_t)gridDim.x * 4) {
+    es[wl][lane] = enc[b * 64 + lane];
+    es[wl][lane + 32] = enc[b * 64 + 32 + lane];
+    __syncwarp();
+    float a0 = b1[lane], a1 = b1[lane + 32];
 #pragma unroll 8
-  for (int k = 0; k < 64; ++k) {
-    float e = es[wl][k];
-    a0 = fmaf(w1s[k][lane], e, a0);
-    a1 = fmaf(w1s[k][lane + 32], e, a1);
-  }
-  hs[wl][lane] = fmaxf(a0, 0.f);
-  hs[wl][lane + 32] = fmaxf(a1, 0.f);
-  __syncwarp();
-  float z[2] = {0.f, 0.f};
-  for (int o = 0; o < n_out; ++o) {
-    float p = w2[o * 64 + lane] * hs[wl][lane];
-    p = fmaf(w2[o * 64 + 32 + lane], hs[wl][lane + 32], p);
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) p += __shfl_xor_sync(0xffffffffu, p, s);
-    z[o] = p + b2[o];
-  }
-  if (live && lane == 0) {
-    if (n_out == 1) {
-      float p = sigmoid_f(z[0]);
-      if (out) out[b] = p;
-      if (post) post[b] = p;
-    } else {
-      float m = fmaxf(z[0], z[1]);
-      float e0 = expf(z[0] - m), e1 = expf(z[1] - m);
-      float s = e0 + e1;
-      if (out) { out[b * 2] = e0 / s; out[b * 2 + 1] = e1 / s; }
-      if (post) post[b] = e1 / s;
+    for (int k = 0; k < 64; ++k) {
+      float e = es[wl][k];
+      a0 = fmaf(w1s[k][lane], e, a0);
+      a1 = fmaf(w1s[k][lane + 32], e, a1);
     }
+    hs[wl][lane] = fmaxf(a0, 0.f);
+    hs[wl][lane + 32] = fmaxf(a1, 0.f);
+    __syncwarp();
+    float z[2] = {0.f, 0.f};
+    for (int o = 0; o < n_out; ++o) {
+      float p = w2[o * 64 + lane] * hs[wl][lane];
+      p = fmaf(w2[o * 64 + 32 + lane], hs[wl][lane + 32], p);
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) p += __shfl_xor_sync(0xffffffffu, p, s);
+      z[o] = p + b2[o];
+    }
+    if (lane == 0) {
+      if (n_out == 1) {
+        float p = sigmoid_f(z[0]);
+        if (out) out[b] = p;
+        if (post) post[b] = p;
+      } else {
+        float m = fmaxf(z[0], z[1]);
+        float e0 = expf(z[0] - m), e1 = expf(z[1] - m);
+        float s = e0 + e1;
+        if (out) { out[b * 2] = e0 / s; out[b * 2 + 1] = e1 / s; }
+        if (post) post[b] = e1 / s;
+      }
+    }
+    __syncwarp();
   }
+}
+
+static unsigned detect_grid(const wwb_ctx* ctx, int64_t B) {
+  return (unsigned)std::min<int64_t>((B + 3) / 4, (int64_t)ctx->sm_count * 16);
 }
 
 int crnn_simt_detect(wwb_ctx* ctx, const float* enc, int64_t B, float* out, cudaStream_t st) {
   if (B == 0) return WWB_OK;
   const CrnnWeights& W = ctx->crnn;
-  crnn_detect_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(enc, W.det1_w, W.det1_b, W.det2_w, W.det2_b,
+  crnn_detect_kernel<<<detect_grid(ctx, B), 128, 0, st>>>(enc, W.det1_w, W.det1_b, W.det2_w, W.det2_b,
                                                              ctx->n_out, out, nullptr, B, nullptr);
   WWB_CHECK_LAUNCH(ctx);
   return WWB_OK;
@@ -284,7 +292,7 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
       WWB_CHECK_LAUNCH(ctx);
     }
     if (det_out || post) {
-      crnn_detect_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, st>>>(
+      crnn_detect_kernel<<<detect_grid(ctx, nb), 128, 0, st>>>(
           enc, W.det1_w, W.det1_b, W.det2_w, W.det2_b, ctx->n_out,
           det_out ? det_out + b0 * ctx->n_out : nullptr, post ? post + b0 : nullptr, nb, wm.n_win_dev);
       WWB_CHECK_LAUNCH(ctx);
