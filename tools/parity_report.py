@@ -23,3 +23,19 @@ for wname, name in (("CRNN", "crnn"), ("CRNN_arik_original", "crnn"), ("Wavenet"
         flips = int(((post > 0.5) != (ref > 0.5))[~band].sum())
         print("%-20s %-8s windows %4d  max |enc err| %.2e  max |posterior err| %.2e  decision flips outside the band %d"
               % (wname, prec, X.shape[0], np.abs(enc - ref_enc).max(), np.abs(post - ref).max(), flips))
+
+# sliding windows (hop 2, get_posterior semantics): the CRNN tensor-core path shares conv / GRU-1 projection columns
+# between the overlapping windows of a stream here (crnn_tc.cu, CrnnShare)
+from wakeword_detection_b200 import synth
+for wname in ("CRNN", "Wavenet"):
+    w = load_weights(wname)
+    L = int(w["mel_length"])
+    mels = np.stack([R.mel_stream(np.clip(synth.stream_float(16000 * 6, c, 5, c), -1, 1).astype(np.float32), w)
+                     for c in range(synth.N_CLASSES)])
+    nw = R.eval_windows(mels.shape[1], L)
+    j = np.arange(0, nw, 7)
+    ref = np.stack([R.posterior(m[(2 * j)[:, None] + np.arange(L)[None, :]], w) for m in mels])
+    for prec in ("f32", "tc"):
+        post = get_engine(wname, prec).posteriors(mels, hop=2).cpu().numpy()[:, j]
+        print("%-20s %-8s sliding hop-2 windows %d streams x %d (every 7th checked)  max |posterior err| %.2e"
+              % (wname, prec, mels.shape[0], nw, np.abs(post - ref).max()))
