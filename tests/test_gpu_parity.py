@@ -546,3 +546,41 @@ def test_tf_lite_opts_models_predict_dropin(wname, name):
         ETO.models_predict(enc, det, X.astype(np.float64), wname)
     with pytest.raises(ValueError):
         ETO.models_predict(enc, det, X, "Wavenet" if wname == "CRNN" else "CRNN")
+
+
+def test_dataset_filter_dropin(tmp_path, w_crnn):
+    """utils/filter_dataset_to_h5.py:65-143: clips padded to whole 20 ms frames, ONE filter window carried across clips,
+    empty clips dropped, features + attributes per clip; batched through the CUDA filter kernel."""
+    import json
+    import os
+    from conftest import WEIGHTS
+    from wakeword_detection_b200 import evaluate_tf_lite_opts as ETO
+    from wakeword_detection_b200.filter_dataset import Dataset_Filter
+    clips = [np.clip(synth.stream_float(n, c, 3, c), -1, 1).astype(np.float32) if n else np.zeros((0,), np.float32)
+             for c, n in enumerate((16000, 9001, 333, 0, 24000))]
+    meta = [{"audio_file_path": "audio/c%d.wav" % i, "is_hotword": i % 2, "worker_id": "w%d" % (i % 3)} for i in range(len(clips))]
+    js = str(tmp_path / "test.json")
+    json.dump(meta, open(js, "w"))
+    df = Dataset_Filter(js, None, wake_word="hey-snips", sample_rate=16000, frame_width=20, hop_width=10,
+                        out_dir=str(tmp_path / "out"), data_dir=str(tmp_path), models_dir=os.path.join(WEIGHTS, "CRNN"),
+                        vad=lambda frame_bytes, sr: np.abs(np.frombuffer(frame_bytes, np.int16)).max() > 2000)
+    recs = df.filter_clips(clips, [m["is_hotword"] for m in meta], [m["audio_file_path"] for m in meta])
+    assert recs[3] is None and [r["file_name"] for r in recs if r] == ["c0", "c1", "c2", "c4"]
+    # oracle: the padded clips back to back through one window (the reference's single Filter instance)
+    padded = [np.pad(c, (0, -len(c) % 320)) for c in clips if len(c)]
+    ref = R.mel_stream(np.concatenate(padded), w_crnn)
+    rows = [(len(padded[0]) - 512) // 160 + 1] + [len(p) // 160 for p in padded[1:]]
+    assert [r["features"].shape[0] for r in recs if r] == rows and sum(rows) == ref.shape[0]
+    got = np.concatenate([r["features"] for r in recs if r])
+    check_mel(got, ref)
+    assert recs[0]["speech_start_ts"] >= 0 and recs[0]["speech_end_ts"] > recs[0]["speech_start_ts"]
+    # whole-dataset path with array clips: write the npz twin and read it back with the evaluation loader
+    df2 = Dataset_Filter(js, None, out_dir=str(tmp_path / "out"), data_dir="", models_dir=os.path.join(WEIGHTS, "CRNN"), vad=None)
+    recs2 = [r for r in df2.filter_clips(clips, [m["is_hotword"] for m in meta], [m["audio_file_path"] for m in meta]) if r]
+    for r, m in zip(recs2, [m for m, c in zip(meta, clips) if len(c)]):
+        r["speaker"] = df2.speakers_dict[m["worker_id"]]
+    path = df2.write_npz(recs2)
+    X, y = ETO.load_data(path, 151, 40)
+    assert X.shape == (4, 151, 40) and list(y) == [0, 1, 0, 0]
+    assert np.array_equal(X[0, :rows[0]], recs2[0]["features"][:151]) and recs2[0]["speech_start_ts"] == -1
+    assert df2.speakers_dict == {"w0": 0, "w1": 1, "w2": 2}

@@ -593,8 +593,7 @@ struct GrParams {
   const float* xw;              // [ceil(B/128), 19, 48, 128] float4
   const float* xws;             // shared-column mode (else null): [3 variants][stream][48][Mp] float4 by position (CrnnShare)
   size_t xws_variant;           // bytes between two variants
-  int q, Mp, wps, tps;          // shared-column geometry (CaShare); tiles are then per stream: tile = stream*tps + j/128
-  int64_t n_tiles;
+  int q, Mp, wps;               // shared-column geometry (CrnnShare)
   const unsigned char* u;       // [2][GR_U_BYTES] packed
   const float* bh;              // [2][32]  recurrent bias of the candidate gate
   float* seq_out;               // [B, 19, 64] or null
@@ -636,7 +635,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role branches are uniform branches
   const int64_t n_win = P.n_win_dev ? (int64_t)*P.n_win_dev : P.n_win;
   const bool shared = P.xws != nullptr;
-  const int64_t n_tiles = shared ? P.n_tiles : (n_win + 127) / 128;
+  const int64_t n_tiles = (n_win + 127) / 128;
 
   for (int i = tid; i < (int)(2 * GR_U_BYTES / 16); i += GR_THREADS)
     reinterpret_cast<uint4*>(&sm.u[0][0])[i] = reinterpret_cast<const uint4*>(P.u)[i];
@@ -663,14 +662,8 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
     const float* bh = sm.bh[d];
     uint32_t n_acc = 0, n_x = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      int64_t b = tile * 128 + r;
-      bool valid = b < n_win;
-      if (shared) {
-        const int64_t stream = tile / P.tps;
-        const int j = (int)(tile - stream * P.tps) * 128 + r;
-        b = stream * P.wps + j;
-        valid = j < P.wps;
-      }
+      const int64_t b = tile * 128 + r;
+      const bool valid = b < n_win;
       float h[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) h[i] = 0.f;
@@ -772,18 +765,26 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
         if (!__shfl_sync(0xffffffffu, ok, 0)) return;
       }
       const int t = dd ? GR_T - 1 - ld_s[dd] : ld_s[dd];
-      if (lane == 0) mbar_arrive_expect_tx(&sm.x_full[dd][xs], GR_X_BYTES);
-      __syncwarp();
       if (shared) {
-        // 128 consecutive positions (windows j0.. at step t sit at m = j0 + q*t ..) of 24 column rows; the padded
+        // the tile's windows b0.. are dense over (stream, j): at step t they sit at consecutive positions m = j + q*t of
+        // their stream, so a slab is one run of positions per stream the tile touches, times 24 column rows; the padded
         // columns t = 0 / 18 come from their own variants of the strip computation
-        const int64_t stream = ld_tile[dd] / P.tps;
-        const int j0 = (int)(ld_tile[dd] - stream * P.tps) * 128;
+        const int64_t b0 = ld_tile[dd] * 128;
+        const int nrows = (int)(n_win - b0 < 128 ? n_win - b0 : 128);
+        if (lane == 0) mbar_arrive_expect_tx(&sm.x_full[dd][xs], (uint32_t)nrows * 24 * 16);
+        __syncwarp();
+        int64_t stream = b0 / P.wps;
+        int j = (int)(b0 - stream * P.wps);
         const unsigned char* base = reinterpret_cast<const unsigned char*>(P.xws) + (t == 0 ? 1 : t == GR_T - 1 ? 2 : 0) * P.xws_variant;
-        if (lane < 24)
-          bulk_g2s(sm.x[dd][xs] + lane * 2048, base + (((size_t)stream * 48 + dd * 24 + lane) * P.Mp + j0 + P.q * t) * 16, 2048,
-                   &sm.x_full[dd][xs]);
+        for (int row = 0; row < nrows; ++stream, j = 0) {
+          const int n = nrows - row < P.wps - j ? nrows - row : P.wps - j;
+          if (lane < 24)
+            bulk_g2s(sm.x[dd][xs] + (lane * 128 + row) * 16, base + (((size_t)stream * 48 + dd * 24 + lane) * P.Mp + j + P.q * t) * 16,
+                     (uint32_t)n * 16, &sm.x_full[dd][xs]);
+          row += n;
+        }
       } else if (lane == 0) {
+        mbar_arrive_expect_tx(&sm.x_full[dd][xs], GR_X_BYTES);
         bulk_g2s(sm.x[dd][xs], reinterpret_cast<const unsigned char*>(P.xw) + ((size_t)(ld_tile[dd] * GR_T + t) * 48 + dd * 24) * 128 * 16,
                  GR_X_BYTES, &sm.x_full[dd][xs]);
       }
@@ -848,11 +849,9 @@ int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* 
   int64_t n_tiles = (B + 127) / 128;
   if (xws) {
     P.xws = xws;
-    P.q = g->q; P.Mp = g->Mp; P.wps = g->wps; P.tps = g->tps;
+    P.q = g->q; P.Mp = g->Mp; P.wps = g->wps;
     P.xws_variant = crnn_share_xws_bytes(*g, B / g->wps);
-    n_tiles = (B / g->wps) * g->tps;
   }
-  P.n_tiles = n_tiles;
   P.u = ctx->crnn.tc_u[layer];
   P.bh = ctx->crnn.tc_bh[layer];
   P.seq_out = seq_out;

@@ -49,7 +49,7 @@ def load_data(data_file, timesteps, num_features) -> Tuple[np.ndarray, np.ndarra
     labels: List[int] = []
     if str(data_file).endswith(".npz"):
         with np.load(data_file) as z:
-            keys = [k for k in z.files if not k.endswith(_LABEL)]
+            keys = [k for k in z.files if '/' not in k]      # '<key>/<attr>' entries are the attributes
             X = np.zeros((len(keys), timesteps, num_features), dtype=np.float32)
             for i, key in enumerate(keys):
                 labels.append(int(z[key + _LABEL]))
