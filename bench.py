@@ -425,7 +425,7 @@ def main():
         # Sliding windows share the conv + GRU-1 projection columns (crnn_tc.cu, CrnnShare): the figures above use the
         # ALGORITHMIC flops of the per-window formulation; these are the flops the kernels execute.
         q = 4                                                     # hop 2: position indices per conv step
-        nsp = -(-((nwin["CRNN"] - 1 + 17 * q) // q + 1) // 126)   # strips of 126 conv steps per stream and phase
+        nsp = -(-((nwin["CRNN"] - 1 + 18 * q) // q + 1) // 126)   # strips of 126 conv steps per stream and phase
         cols = 3 * q * nsp * 126                                  # interior + two padded-column variants
         exe = cols * (2432000 + 4669440) / 19.0 / nwin["CRNN"] + 2 * 233472 + 466944 + 8320
         extra["CRNN_shared_columns"] = {"executed_flop_per_window": exe,

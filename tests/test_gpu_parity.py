@@ -502,7 +502,8 @@ def test_encoders_are_deterministic(wname):
             assert torch.equal(eng.posteriors(mel, 2), ref)
 
 
-@pytest.mark.parametrize("S,F,hop", [(2, 411, 2), (5, 998, 2), (2, 700, 1), (3, 600, 4), (2, 1200, 8), (1, 153, 2), (40, 998, 2)])
+@pytest.mark.parametrize("S,F,hop", [(2, 411, 2), (5, 998, 2), (2, 700, 1), (3, 600, 4), (2, 1200, 8), (1, 153, 2), (40, 998, 2),
+                                     (2, 1015, 2), (2, 1015, 1), (2, 1021, 2), (3, 151 + 2 * 72, 2)])   # 1015: column t = 18 of the last windows is the strip's last row
 def test_crnn_shared_columns_bit_identical_to_per_window_path(S, F, hop):
     """Sliding-window batches compute every conv / GRU-1 projection column once per stream position (crnn_tc.cu,
     CrnnShare); WWB_CRNN_NO_SHARE=1 forces the per-window tiles.  Same MMAs on the same operands: identical bits."""

@@ -6,7 +6,7 @@ from conftest import get_engine
 tc = get_engine("CRNN", "tc"); f32 = get_engine("CRNN", "f32")
 ok = True
 import sys as _s
-SHAPES = [(1, 30000, 2), (3, 151 + 2 * 72, 2), (2, 151 + 127 * 2, 2), (2, 151 + 128 * 2, 2), (1, 9000, 1), (1000, 300, 2), (3, 5000, 4), (2, 9000, 8), (149, 998, 2)] if len(_s.argv) > 1 and _s.argv[1] == 'edge' else None
+SHAPES = [(1, 30000, 2), (3, 151 + 2 * 72, 2), (2, 151 + 127 * 2, 2), (2, 151 + 128 * 2, 2), (1, 9000, 1), (1000, 300, 2), (3, 5000, 4), (2, 9000, 8), (149, 998, 2), (2, 1015, 2), (2, 1015, 1), (2, 1017, 2), (2, 1023, 2), (3, 2023, 2)] if len(_s.argv) > 1 and _s.argv[1] == 'edge' else None
 for (S, F, hop) in SHAPES or [(3, 200, 2), (2, 151 + 2 * 130, 2), (5, 998, 2), (2, 700, 1), (3, 600, 4), (2, 1200, 8), (1, 153, 2), (7, 2000, 2), (90, 998, 2)]:
     torch.manual_seed(S * 1000 + F)
     X = torch.rand((S, F, 40), device=tc.device) * 5

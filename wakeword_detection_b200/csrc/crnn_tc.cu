@@ -512,7 +512,7 @@ bool crnn_share_plan(const WinMap& wm, int L, CrnnShare* out) {
   g.wps = wps;
   g.tps = (wps + 127) / 128;
   g.F = (wps - 1) * hop + L;
-  const int m_max = wps - 1 + 17 * g.q;
+  const int m_max = wps - 1 + 18 * g.q;   // column t = 18 of the last window (variant 2 strips)
   g.nsp = (m_max / g.q + 1 + CA_STRIP_ROWS - 1) / CA_STRIP_ROWS;
   g.Mp = g.q * CA_STRIP_ROWS * g.nsp;
   g.n_streams = wm.n_win / wps;
