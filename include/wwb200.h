@@ -111,7 +111,7 @@ int64_t wwb_num_frames(int64_t n_samples);
 int64_t wwb_num_windows(const wwb_ctx* ctx, int64_t n_frames, int hop);
 /* Scheduling hint for callers that feed wwb_posteriors / wwb_pipeline in slices of streams (e.g. to overlap host->device
  * copies with compute): slices whose stream count is a multiple of the returned granule fill whole waves of the
- * persistent kernels (CRNN: 128-window recurrence tiles per stream against the SM count).  1 if there is no preference.
+ * persistent kernels (CRNN: strip tiles per stream against the SM count).  1 if there is no preference.
  * No reference counterpart (the TFLite path is batch-1). */
 int64_t wwb_stream_granule(const wwb_ctx* ctx, int64_t n_frames, int hop);
 

@@ -339,10 +339,16 @@ int64_t wwb_num_windows(const wwb_ctx* ctx, int64_t n_frames, int hop) {
 
 int64_t wwb_stream_granule(const wwb_ctx* ctx, int64_t n_frames, int hop) {
   if (!ctx || ctx->kind != WWB_MODEL_CRNN || ctx->precision == WWB_PREC_F32) return 1;
-  const int64_t wps = wwb_num_windows(ctx, n_frames, hop);
-  if (wps < 1) return 1;
-  const int64_t tps = (wps + 127) / 128;   // layer-1 recurrence tiles per stream (crnn_tc.cu, CrnnShare)
-  return ctx->sm_count % tps == 0 ? ctx->sm_count / tps : 1;
+  WinMap wm;
+  memset(&wm, 0, sizeof(wm));
+  wm.win_per_stream = (int)wwb_num_windows(ctx, n_frames, hop);
+  wm.n_win = wm.win_per_stream;
+  wm.hop = hop;
+  wm.ring = (int)n_frames;
+  CrnnShare g;
+  if (wm.win_per_stream < 1 || !crnn_share_plan(wm, ctx->L, &g)) return 1;
+  const int64_t per_stream = (int64_t)g.q * g.nsp;   // strip tiles per stream and conv-weight variant (crnn_tc.cu)
+  return ctx->sm_count % per_stream == 0 ? ctx->sm_count / per_stream : 1;
 }
 
 int wwb_filter(wwb_ctx* ctx, const void* pcm, int dtype, int64_t S, int64_t N, int64_t pitch, float a, float* mel,
