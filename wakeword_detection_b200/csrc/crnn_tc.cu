@@ -5,9 +5,12 @@
 //     mel window [151,40]  ->  xw1[b, t, 0:192] = conv_out[b, t, 0:640] . W1^T + b_in
 // (fwd gates z|r|h then bwd gates z|r|h).  The 48.6 KB/window conv output never leaves the SM.
 //
-// One persistent CTA per SM works on tiles of 6 windows.  Row r = wl*21 + t of a tile
-// (wl = window in the tile, t = conv time step; 19 of every 21 rows are real) is the M index
-// of every GEMM, so one thread owns one (window, t) pair.
+// One persistent CTA per SM works on tiles of 128 GEMM rows.  For independent windows a tile is 6 windows: row
+// r = wl*21 + t (wl = window in the tile, t = conv time step; 19 of every 21 rows are real) is the M index of every
+// GEMM, so one thread owns one (window, t) pair.  For sliding-window batches a tile is a STRIP of 126 consecutive conv
+// steps of one stream (CA_MODE_STRIPS below): every column is computed once per stream position instead of once per
+// window that contains it.  Everything between the producers (which frames an element holds) and the projection
+// epilogue (where a row's xw goes) is the same code in both modes.
 //
 //  * The conv is an implicit GEMM per output frequency f: D[128,32] = A_f[128,128] . Wc^T with
 //    k = (freq tap kf, time tap kt).  A_f is never materialised: the window is kept in shared
