@@ -631,6 +631,12 @@ __device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ldN(uint32_t taddr, float (&v)[8]) { tmem_ld8f(taddr, v); }
+__device__ __forceinline__ void tmem_ldN(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+#ifndef GR_CHUNKS
+#define GR_CHUNKS 2                                // the epilogue processes the 32 units in this many pieces (2: 2.94 -> 2.90 ms CRNN stage against 4)
+#endif
+
 __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GrSmem& sm = *reinterpret_cast<GrSmem*>(smem_raw);
@@ -684,31 +690,34 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
           fence_after_sync();
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float4 xc[6];
-          xc[0] = xp[(2 * u) * 128]; xc[1] = xp[(2 * u + 1) * 128];
-          xc[2] = xp[(2 * u + 8) * 128]; xc[3] = xp[(2 * u + 9) * 128];
-          xc[4] = xp[(2 * u + 16) * 128]; xc[5] = xp[(2 * u + 17) * 128];
-          if (u == 3) x_last = xc[5].w;
-          float hz[8], hr[8], hh[8];
+        for (int u = 0; u < GR_CHUNKS; ++u) {
+          constexpr int CW = 32 / GR_CHUNKS, C4 = CW / 4;   // units / float4 columns per chunk and gate
+          float4 xc[3][C4];
+#pragma unroll
+          for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int i = 0; i < C4; ++i) xc[g][i] = xp[(g * 8 + u * C4 + i) * 128];
+          if (u == GR_CHUNKS - 1) x_last = xc[2][C4 - 1].w;
+          float hz[CW], hr[CW], hh[CW];
           if (s > 0) {
-            tmem_ld8f(tbase + u * 8, hz);
-            tmem_ld8f(tbase + 32 + u * 8, hr);
-            tmem_ld8f(tbase + 64 + u * 8, hh);
+            tmem_ldN(tbase + u * CW, hz);
+            tmem_ldN(tbase + 32 + u * CW, hr);
+            tmem_ldN(tbase + 64 + u * CW, hh);
             tmem_ld_wait();
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { hz[i] = 0.f; hr[i] = 0.f; hh[i] = 0.f; }
+            for (int i = 0; i < CW; ++i) { hz[i] = 0.f; hr[i] = 0.f; hh[i] = 0.f; }
           }
-          const float xz[8] = {xc[0].x, xc[0].y, xc[0].z, xc[0].w, xc[1].x, xc[1].y, xc[1].z, xc[1].w};
-          const float xr[8] = {xc[2].x, xc[2].y, xc[2].z, xc[2].w, xc[3].x, xc[3].y, xc[3].z, xc[3].w};
-          const float xh[8] = {xc[4].x, xc[4].y, xc[4].z, xc[4].w, xc[5].x, xc[5].y, xc[5].z, xc[5].w};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float z = sigmoid_fast(xz[i] + hz[i]);
-            const float rr = sigmoid_fast(xr[i] + hr[i]);
-            const float c = tanh_fast(fmaf(rr, hh[i] + bh[u * 8 + i], xh[i]));
-            h[u * 8 + i] = fmaf(z, h[u * 8 + i] - c, c);
+          for (int i = 0; i < CW; ++i) {
+            const float4 vz = xc[0][i >> 2], vr = xc[1][i >> 2], vh = xc[2][i >> 2];
+            const float xz = (i & 3) == 0 ? vz.x : (i & 3) == 1 ? vz.y : (i & 3) == 2 ? vz.z : vz.w;
+            const float xr = (i & 3) == 0 ? vr.x : (i & 3) == 1 ? vr.y : (i & 3) == 2 ? vr.z : vr.w;
+            const float xh = (i & 3) == 0 ? vh.x : (i & 3) == 1 ? vh.y : (i & 3) == 2 ? vh.z : vh.w;
+            const float z = sigmoid_fast(xz + hz[i]);
+            const float rr = sigmoid_fast(xr + hr[i]);
+            const float c = tanh_fast(fmaf(rr, hh[i] + bh[u * CW + i], xh));
+            h[u * CW + i] = fmaf(z, h[u * CW + i] - c, c);
           }
         }
         // hand the stage back once every lane's loads from it have completed (the arrive depends on the last loaded
@@ -883,6 +892,9 @@ int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* 
 constexpr int G2_W_BYTES = 2 * 8 * 96 * 16;        // per direction: hi + lo planes, K = 64, N = 96
 constexpr int G2_BIAS_BYTES = 2 * 96 * 16;         // B operand of the 'ones' k-step
 constexpr int G2_AST = 2;                          // A slab stages per direction
+#ifndef G2_CHUNKS
+#define G2_CHUNKS 2                                // the epilogue reads the accumulator in this many pieces (2: 2.97 -> 2.92 ms CRNN stage against 4)
+#endif
 
 struct G2Smem {
   unsigned char a[2][G2_AST][G2_A_BYTES];
@@ -970,29 +982,30 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru2_fused_tc_kernel(const G2Pa
         mbar_wait(&sm.acc_full[d], n_acc & 1);
         fence_after_sync();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float xh[8], az[8], ar[8], hh[8];
-          tmem_ld8f(tbase + u * 8, xh);
-          tmem_ld8f(tbase + 32 + u * 8, az);
-          tmem_ld8f(tbase + 64 + u * 8, ar);
+        for (int u = 0; u < G2_CHUNKS; ++u) {
+          constexpr int CW = 32 / G2_CHUNKS;   // units per chunk
+          float xh[CW], az[CW], ar[CW], hh[CW];
+          tmem_ldN(tbase + u * CW, xh);
+          tmem_ldN(tbase + 32 + u * CW, az);
+          tmem_ldN(tbase + 64 + u * CW, ar);
           if (s > 0) {
-            tmem_ld8f(tbase + 96 + u * 8, hh);
+            tmem_ldN(tbase + 96 + u * CW, hh);
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) hh[i] = 0.f;
+            for (int i = 0; i < CW; ++i) hh[i] = 0.f;
           }
           tmem_ld_wait();
-          if (u == 3) {   // the accumulator has been read: the next step's input projection may overwrite it
+          if (u == G2_CHUNKS - 1) {   // the accumulator has been read: the next step's input projection may overwrite it
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.acc_free[d]);
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < CW; ++i) {
             const float z = sigmoid_fast(az[i]);
             const float rr = sigmoid_fast(ar[i]);
-            const float c = tanh_fast(fmaf(rr, hh[i] + bh[u * 8 + i], xh[i]));
-            h[u * 8 + i] = fmaf(z, h[u * 8 + i] - c, c);
+            const float c = tanh_fast(fmaf(rr, hh[i] + bh[u * CW + i], xh[i]));
+            h[u * CW + i] = fmaf(z, h[u * CW + i] - c, c);
           }
         }
         if (s < GR_T - 1) {
