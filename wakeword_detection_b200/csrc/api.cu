@@ -218,9 +218,7 @@ static int build_wavenet(wwb_ctx* ctx, const wwb_weights* w) {
                                                             w->bn_add, N.dilation);
     if (blocks.empty()) return fail(ctx, WWB_ERR_ARG, "WaveNet: a BatchNorm scale of 0 cannot be folded into the tensor-core path (use precision f32)");
     if ((rc = upload(ctx, blocks, &N.tc_blocks))) return rc;
-    std::vector<float> in_w_kc = transposed(w->in_w, 16, 40);
-    std::vector<unsigned char> head = wavenet_pack_head(in_w_kc.data(), w->in_b, w->bn_mul, w->bn_add, w->det1_w,
-                                                        w->det1_b, w->det2_w, w->det2_b);
+    std::vector<unsigned char> head = wavenet_pack_head(w->bn_mul, w->bn_add, w->det1_w, w->det1_b, w->det2_w, w->det2_b);
     if (head.empty()) return fail(ctx, WWB_ERR_ARG, "WaveNet: a BatchNorm scale of 0 cannot be folded into the tensor-core path (use precision f32)");
     if ((rc = upload(ctx, head, &N.tc_head))) return rc;
   }
@@ -367,6 +365,7 @@ static WinMap batch_map(const wwb_ctx* ctx, const float* mel, int64_t S, int64_t
   wm.n_win = S * wm.win_per_stream;
   wm.hop = hop;
   wm.ring = (int)F;
+  wm.n_streams = S;
   return wm;
 }
 
@@ -496,6 +495,7 @@ int wwb_stream_push(wwb_ctx* ctx, const int16_t* pcm, int64_t S, int64_t n, cons
   wm.win_start = ctx->st.win_start;
   wm.n_win_dev = ctx->st.n_win;
   wm.n_win = S * ctx->st.max_frames;
+  wm.n_streams = S;
   wm.win_per_stream = 1;
   wm.hop = 1;
   wm.ring = ctx->st.ring;

@@ -168,6 +168,7 @@ struct WinMap {
   int win_per_stream;         // regular grid: stream = b / wps, start = (b % wps)*hop
   int hop;
   int ring;                   // rows per stream
+  int64_t n_streams;          // streams behind `mel` (rows = n_streams * ring)
 };
 
 int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out,
@@ -200,9 +201,8 @@ int wavenet_tc_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float*
 std::vector<unsigned char> wavenet_pack_blocks(const float* gate_w, const float* gate_b, const float* rs_w,
                                                const float* rs_b, const float* bn_mul, const float* bn_add,
                                                const int* dilation);
-std::vector<unsigned char> wavenet_pack_head(const float* in_w_kc, const float* in_b, const float* bn_mul0,
-                                             const float* bn_add0, const float* det1_w_nk, const float* det1_b,
-                                             const float* det2_w, const float* det2_b);
+std::vector<unsigned char> wavenet_pack_head(const float* bn_mul0, const float* bn_add0, const float* det1_w_nk,
+                                             const float* det1_b, const float* det2_w, const float* det2_b);
 int wavenet_simt_detect(wwb_ctx* ctx, const float* enc, int64_t B, float* out, cudaStream_t st);
 
 int launch_eval_counts(wwb_ctx* ctx, const float* post, const int64_t* seg_off, int64_t n_seg,

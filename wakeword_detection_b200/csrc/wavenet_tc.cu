@@ -15,8 +15,9 @@
 //   res/skip    D[128,48] = g[128,16] * [Wres | Wskip]       (A from TMEM, own accumulator columns)
 //   epilogue 2a x += ReLU(res); u = BN_next(x) -> hi/lo -> shared memory + TMEM   (releases the next gate GEMM)
 //   epilogue 2b skip += ReLU(.)                                                   (overlaps that GEMM)
-// The input 1x1 conv (mel rows as three fp16 hi/lo k-chunks in TMEM) and the detect head (32->32 with A from
-// TMEM; then 32->2, max over time, softmax) are tensor-core GEMMs of the same kind at the group boundaries.
+// The input 1x1 conv depends only on the mel row, which ~91 overlapping windows share: wn_input_kernel computes it once
+// per row (fp32) and a group starts by loading its rows' 16 values.  The detect head (32->32 with A from TMEM; then
+// 32->2, max over time, softmax) is a tensor-core GEMM of the same kind as the blocks' at the end of a group.
 // Biases are added by the tensor core too: one extra k-step whose A chunk is the constant (1, 1, 0, ...)
 // and whose B rows hold (bias_hi, bias_lo, 0, ...) - broadcast loads of per-block constants from shared
 // memory cost one wavefront per 4 bytes and were the largest shared-memory consumer (profiles/).
@@ -77,8 +78,6 @@ struct WnHead {
   float det2_b[2];
   float pad_[2];
   unsigned char det1_B[2 * 4 * 32 * 16];   // hi/lo planes, 4 chunks x 32 rows x 16 B
-  unsigned char in_B[2 * 6 * 16 * 16];     // input 1x1 conv 40(+8 zero)->16: hi/lo planes, 6 chunks x 16 rows x 16 B
-  unsigned char in_bias_B[2 * 16 * 16];    // its bias for the 'ones' k-step: chunk 0 = (hi, lo, 0...), chunk 1 = 0
 };
 
 struct WnSmem {
@@ -88,7 +87,6 @@ struct WnSmem {
   uint64_t bar_gate[WN_NT], bar_rs[WN_NT], bar_det[WN_NT];   // GEMM completion (tcgen05.commit) -> the tile's four warps
   uint64_t bar_u[WN_NT];                     // the tile's four warps finished epilogue 2 -> gate warp
   uint64_t bar_g[WN_NT];                     // the tile's four warps finished epilogue 1 -> res/skip warp
-  uint64_t bar_in_rdy[WN_NT], bar_in[WN_NT]; // input layer: mel rows stored to TMEM -> gate warp ; its GEMM completed
   uint64_t wfull[WN_WST];
   uint32_t tmem_base;
   int zmax[2][WN_G][2];                      // per-window max of the two logits, double-buffered by group parity
@@ -98,6 +96,7 @@ struct WnTcParams {
   WinMap wm;
   const unsigned char* wblob;   // [24][WN_WBLK]
   const WnHead* head;
+  const float* x0;              // [n_streams * ring][16]: ReLU(in_w * mel + in_b) of every mel row (wn_input_kernel)
   int L;
   int nsplit;
   int dil[24];                  // dilation per block (kernel-parameter space keeps it in uniform registers)
@@ -185,7 +184,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
   if (tid == 0) {
     for (int i = 0; i < WN_NT; ++i) {
       mbar_init(&sm.bar_u[i], 4); mbar_init(&sm.bar_g[i], 4); mbar_init(&sm.bar_gate[i], 1); mbar_init(&sm.bar_rs[i], 1);
-      mbar_init(&sm.bar_det[i], 1); mbar_init(&sm.bar_in_rdy[i], 4); mbar_init(&sm.bar_in[i], 1);
+      mbar_init(&sm.bar_det[i], 1);
     }
     for (int s = 0; s < WN_WST; ++s) mbar_init(&sm.wfull[s], 1);
     mbar_fence_init();
@@ -230,15 +229,23 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     }
     const u64 ZERO2 = pk(0.f, 0.f), ONE2 = pk(1.f, 1.f);
 
-    // The mel row of the NEXT group is fetched into registers before this group's detect epilogue (x / skip are dead
-    // by then), so its global-memory latency is not on the group-boundary chain.
-    float4 mrow[10];
-    auto fetch_mel = [&](int64_t grp_next) {
+    // The input layer x0 = ReLU(in_w * mel + in_b) depends only on the mel row, and every mel row is shared by ~91
+    // overlapping windows: it is computed once per row by wn_input_kernel (64 B per row instead of 160 B of mel per row
+    // and window), which also takes a tcgen05.st / GEMM / tcgen05.ld round trip off the group-boundary chain.  The row
+    // of the NEXT group is fetched into registers before this group's detect epilogue (x / skip are dead by then), so
+    // its global-memory latency is not on that chain either.
+    float4 xrow[4];
+    auto fetch_x0 = [&](int64_t grp_next) {
       const int64_t bn = grp_next * WN_G + w;
       const bool vn = (grp_next < n_groups) && (w < WN_G) && (t < L) && (bn < n_win);
-      const float4* row = reinterpret_cast<const float4*>(win_row(P.wm, vn ? bn : 0, vn ? t : 0));
+      int64_t s0 = 0;
+      int start = 0;
+      if (vn) win_origin(P.wm, bn, s0, start);
+      int rr = start + (vn ? t : 0);
+      if (rr >= P.wm.ring) rr -= P.wm.ring;
+      const float4* row = reinterpret_cast<const float4*>(P.x0 + (s0 * P.wm.ring + rr) * 16);
 #pragma unroll
-      for (int i = 0; i < 10; ++i) mrow[i] = vn ? __ldg(row + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 4; ++i) xrow[i] = vn ? __ldg(row + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     int64_t fin_grp = -1;
     int fin_zp = 0;
@@ -257,59 +264,26 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       }
       fin_grp = -1;
     };
-    // the row's 40 mel values -> three fp16 hi/lo k-chunks in the (free) res/skip accumulator columns -> gate warp
-    auto store_mel = [&]() {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        uint32_t ar[16];
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          if (c * 4 + j4 < 10) {
-            const float4 m = mrow[c * 4 + j4];
-            split2(pk(m.x, m.y), ar[2 * j4], ar[8 + 2 * j4]);
-            split2(pk(m.z, m.w), ar[2 * j4 + 1], ar[8 + 2 * j4 + 1]);
-          } else {
-            ar[2 * j4] = ar[2 * j4 + 1] = ar[8 + 2 * j4] = ar[8 + 2 * j4 + 1] = 0u;
-          }
-        }
-        tmem_st16(tbase + WN_C_R + 16 * c, ar);
-      }
-      tmem_st_wait();
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.bar_in_rdy[tile]);
-    };
-    if ((int64_t)blockIdx.x < n_groups) fetch_mel(blockIdx.x);
+    if ((int64_t)blockIdx.x < n_groups) fetch_x0(blockIdx.x);
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++n_u) {
       const int64_t b = grp * WN_G + w;
       const bool valid = (w < WN_G) && (t < L) && (b < n_win);
       u64 x[8], skip[16];     // channel pairs
-      // ---- input layer: x = ReLU(in_w * mel + in_b) on the tensor core; u0 = BN_0(x) ----
-      // (as 640 FFMA per row fed by broadcast LDS.128 of the weights it cost ~13 % of the kernel: the loads alone are
-      //  4 shared-memory wavefronts each.)  The row's 40 mel values go to TMEM as three fp16 hi/lo k-chunks (the res/skip
-      //  accumulator columns are free at this point); the gate warp issues D[128,16] = mel * in_w^T (+ bias k-step).
+      // ---- input layer: x = x0 row (prefetched); block 0's BatchNorm is folded into its gate weights ----
       {
-        store_mel();
-        if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 0);   // mel chunks stored
-        finalise();   // previous group's posteriors, while the input GEMM runs
+        if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 0);
+        finalise();   // previous group's posteriors
 #pragma unroll
         for (int n = 0; n < 16; ++n) skip[n] = ZERO2;
-        WN_MBAR_WAIT(&sm.bar_in[tile], n_u & 1, 12);
-        fence_after_sync();
-        if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 1);   // input GEMM done
         uint32_t ur[16];
 #pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          float r[8];
-          tmem_ld8(tbase + WN_C_G + h8 * 8, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const int c = h8 * 4 + p;
-            x[c] = relu2(pk(r[2 * p], r[2 * p + 1]));
-            split2(x[c], ur[c], ur[8 + c]);
-          }
+        for (int i = 0; i < 4; ++i) {
+          x[2 * i] = pk(xrow[i].x, xrow[i].y);
+          x[2 * i + 1] = pk(xrow[i].z, xrow[i].w);
+          split2(x[2 * i], ur[2 * i], ur[8 + 2 * i]);
+          split2(x[2 * i + 1], ur[2 * i + 1], ur[8 + 2 * i + 1]);
         }
+        if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 1);
         if (valid) {
           *reinterpret_cast<uint4*>(Urow) = make_uint4(ur[0], ur[1], ur[2], ur[3]);
           *reinterpret_cast<uint4*>(Urow + WN_PU) = make_uint4(ur[4], ur[5], ur[6], ur[7]);
@@ -441,7 +415,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         }
       }
       if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 0);   // boundary timeline: e2b(23) done
-      fetch_mel(grp + gridDim.x);   // next group's mel row: in flight during the detect epilogue
+      fetch_x0(grp + gridDim.x);   // next group's input row: in flight during the detect epilogue
       // ---- detect head epilogue: ReLU(D + b1) -> 32->2 -> max over time ----
       WN_MBAR_WAIT(&sm.bar_det[tile], n_u & 1, 8);
       fence_after_sync();
@@ -522,33 +496,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       }
     uint32_t n_w = 0;         // global block index (24 per group)
     uint32_t ubase = 0;       // bar_u phases before this group (25 per group)
-    const uint64_t dIn = make_desc(smem_u32(sm.head.in_B), 256, 128);            // input conv B: k-step 0, hi plane
-    const uint64_t dInB = make_desc(smem_u32(sm.head.in_bias_B), 256, 128);      // input conv bias B
-    const uint32_t idesc_in = make_idesc_f16(128, 16);
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ubase += 25, ++n_u) {
-      // input layer: D[128,16] (gate accumulator columns) = mel[128,48] * in_w^T + bias; A = the three k-chunks the
-      // tile's threads stored into the res/skip accumulator columns
-#pragma unroll
-      for (int i = 0; i < WN_NT; ++i) {
-        WN_MBAR_WAIT(&sm.bar_in_rdy[i], n_u & 1, 13);
-        fence_after_sync();
-        if (elect_one()) {
-          const uint32_t tacc = tmem + i * WN_TMEM_TILE;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const uint32_t ta = tacc + WN_C_R + 16 * c;
-            const uint64_t bh = dIn + (uint64_t)((c * 512) >> 4), bl = bh + (uint64_t)(1536 >> 4);
-            mma_f16_ts(tacc + WN_C_G, ta, bh, idesc_in, c != 0);
-            if (nsplit == 3) {
-              mma_f16_ts(tacc + WN_C_G, ta + 8, bh, idesc_in, true);
-              mma_f16_ts(tacc + WN_C_G, ta, bl, idesc_in, true);
-            }
-          }
-          mma_f16_ts(tacc + WN_C_G, tmem + WN_C_ONE, dInB, idesc_in, true);
-          mma_commit(&sm.bar_in[i]);
-        }
-        __syncwarp();
-      }
       for (int k = 0; k < 24; ++k, ++n_w) {
         WN_MBAR_WAIT(&sm.wfull[n_w % WN_WST], (n_w / WN_WST) & 1, 1);
         const uint32_t d = (uint32_t)P.dil[k];
@@ -725,9 +673,8 @@ std::vector<unsigned char> wavenet_pack_blocks(const float* gate_w, const float*
   return out;
 }
 
-std::vector<unsigned char> wavenet_pack_head(const float* in_w_kc, const float* in_b, const float* bn_mul0,
-                                             const float* bn_add0, const float* det1_w_nk, const float* det1_b,
-                                             const float* det2_w, const float* det2_b) {
+std::vector<unsigned char> wavenet_pack_head(const float* bn_mul0, const float* bn_add0, const float* det1_w_nk,
+                                             const float* det1_b, const float* det2_w, const float* det2_b) {
   std::vector<unsigned char> out(sizeof(WnHead), 0);
   WnHead* h = reinterpret_cast<WnHead*>(out.data());
   if (!put_pad_rows(out, offsetof(WnHead, pad0), bn_mul0, bn_add0)) return {};
@@ -735,16 +682,6 @@ std::vector<unsigned char> wavenet_pack_head(const float* in_w_kc, const float* 
   memcpy(h->det1_b, det1_b, sizeof(h->det1_b));
   memcpy(h->det2_w, det2_w, sizeof(h->det2_w));
   memcpy(h->det2_b, det2_b, sizeof(h->det2_b));
-  // input conv B operand: row n = output channel, k = mel bin (40, zero-padded to 48)
-  const size_t ioff = offsetof(WnHead, in_B);
-  for (int n = 0; n < 16; ++n)
-    for (int k = 0; k < 40; ++k) {
-      const int c = k / 8, e = k % 8;
-      const size_t off = ioff + ((size_t)c * 16 + n) * 16 + e * 2;
-      put_split(out, off, off + 1536, in_w_kc[k * 16 + n], true);
-    }
-  const size_t iboff = offsetof(WnHead, in_bias_B);
-  for (int n = 0; n < 16; ++n) put_split(out, iboff + (size_t)n * 16, iboff + (size_t)n * 16 + 2, in_b[n], true);
   const size_t boff = offsetof(WnHead, det1_B);
   for (int n = 0; n < 32; ++n)
     for (int k = 0; k < 32; ++k) {
@@ -755,11 +692,46 @@ std::vector<unsigned char> wavenet_pack_head(const float* in_w_kc, const float* 
   return out;
 }
 
+// Input layer (Wavenet/encode.tflite op 0: 1x1 conv 40 -> 16 + ReLU) once per mel row, fp32:
+// x0[row, c] = ReLU(b[c] + sum_k w[k][c] * mel[row, k]).  4 threads per row, 4 channels each.
+__global__ void __launch_bounds__(256) wn_input_kernel(const float* __restrict__ mel, const float* __restrict__ w_kc,
+                                                       const float* __restrict__ b, float* __restrict__ x0, int64_t n_rows) {
+  __shared__ float ws[kMel * 16];
+  __shared__ float bs[16];
+  for (int i = threadIdx.x; i < kMel * 16; i += 256) ws[i] = w_kc[i];
+  if (threadIdx.x < 16) bs[threadIdx.x] = b[threadIdx.x];
+  __syncthreads();
+  const int c4 = threadIdx.x & 3;
+  for (int64_t row = (int64_t)blockIdx.x * 64 + (threadIdx.x >> 2); row < n_rows; row += (int64_t)gridDim.x * 64) {
+    const float4* m4 = reinterpret_cast<const float4*>(mel + row * kMel);
+    float a0 = bs[4 * c4], a1 = bs[4 * c4 + 1], a2 = bs[4 * c4 + 2], a3 = bs[4 * c4 + 3];
+#pragma unroll
+    for (int k4 = 0; k4 < kMel / 4; ++k4) {
+      const float4 m = __ldg(m4 + k4);
+      const float mv[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 wv = *reinterpret_cast<const float4*>(ws + (4 * k4 + e) * 16 + 4 * c4);
+        a0 = fmaf(wv.x, mv[e], a0); a1 = fmaf(wv.y, mv[e], a1); a2 = fmaf(wv.z, mv[e], a2); a3 = fmaf(wv.w, mv[e], a3);
+      }
+    }
+    reinterpret_cast<float4*>(x0 + row * 16)[c4] = make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
+  }
+}
+
 int wavenet_tc_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out, float* post,
                           cudaStream_t st) {
   if (wm.n_win == 0) return WWB_OK;
   if (ctx->L > 182) return fail(ctx, WWB_ERR_ARG, "tensor-core WaveNet path supports windows up to 182 frames");
+  const int64_t n_rows = wm.n_streams * (int64_t)wm.ring;
+  void* x0;
+  int rc = workspace(ctx, 1, (size_t)std::max<int64_t>(n_rows, 1) * 16 * sizeof(float), &x0);
+  if (rc) return rc;
+  wn_input_kernel<<<(unsigned)std::min<int64_t>((n_rows + 63) / 64, (int64_t)ctx->sm_count * 8), 256, 0, st>>>(
+      wm.mel, ctx->wn.in_w, ctx->wn.in_b, (float*)x0, n_rows);
+  WWB_CHECK_LAUNCH(ctx);
   WnTcParams P;
+  P.x0 = (const float*)x0;
   P.wm = wm;
   P.wblob = ctx->wn.tc_blocks;
   P.head = reinterpret_cast<const WnHead*>(ctx->wn.tc_head);
