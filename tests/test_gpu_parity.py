@@ -2,8 +2,7 @@
 the CPU oracle on the same seeded inputs, against the committed golden vectors from the
 reference's own glue, and — at benchmark sizes — through size-independent properties.
 
-Tolerances: mel |d| <= 1e-4*max(|ref|,1) (bins within a factor 2 of the
-1e-5 energy floor are counted separately with a looser bound); encoder outputs and
+Tolerances: mel |d| <= 1e-4*max(|ref|,1) on every bin (no exemptions); encoder outputs and
 posteriors 1e-3 absolute; trigger decisions and FAR/FRR counts exact.
 """
 import numpy as np
@@ -17,27 +16,32 @@ pytestmark = pytest.mark.gpu
 
 MEL_RTOL = 1e-4
 POST_ATOL = 1e-3
-NEAR_FLOOR = 0.35          # 0.5*ln(2): energy below 2x the floor
-DYN_RANGE = 4.0            # log-mel more than 4.0 below the frame's loudest band (energy ratio > 3000)
-LOOSE_ATOL = 2e-3
+MEL_STATS = {"bins": 0, "at_floor": 0, "max_err": 0.0, "max_err_over_tol": 0.0}
 
 
 def check_mel(got, ref):
-    """Strict bound everywhere except two classes that are reported separately with a looser
-    bound: bands at the 1e-5 energy floor, and bands more than DYN_RANGE below the loudest
-    band of their frame — there the fp32 FFT's rounding noise (relative to the frame's
-    *peak*) is what limits agreement with the reference's fp64 FFT (measured: 4.6e-4 worst
-    case on a full-scale clipping sine, 1e-6 on every other signal class)."""
+    """|d| <= 1e-4 * max(|ref|, 1) on EVERY bin, no exemptions (the FFT is fp64 like the
+    reference's, csrc/fft64.cuh).  Bins whose reference value is exactly 0.0 (energy at or below the 1e-5 floor) are
+    counted, not exempted: they obey the same bound.  Running statistics are printed at the end of the session."""
     got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
     assert got.shape == ref.shape
     tol = MEL_RTOL * np.maximum(np.abs(ref), 1.0)
     err = np.abs(got - ref)
-    loose = (ref < NEAR_FLOOR) | (ref < ref.max(axis=-1, keepdims=True) - DYN_RANGE)
-    assert np.all(err[~loose] <= tol[~loose]), "mel error %.3e over tolerance (worst at ref=%.4f)" % (
-        err[~loose].max(), ref[~loose][np.argmax(err[~loose])])
-    if loose.any():
-        assert err[loose].max() <= LOOSE_ATOL, "floor/dynamic-range-limited mel error %.3e" % err[loose].max()
-    return int(loose.sum())
+    MEL_STATS["bins"] += int(ref.size)
+    MEL_STATS["at_floor"] += int((ref == 0.0).sum())
+    if ref.size:
+        MEL_STATS["max_err"] = max(MEL_STATS["max_err"], float(err.max()))
+        MEL_STATS["max_err_over_tol"] = max(MEL_STATS["max_err_over_tol"], float((err / tol).max()))
+        i = np.unravel_index(np.argmax(err / tol), err.shape)
+        assert np.all(err <= tol), "mel error %.3e over tolerance %.3e (ref=%.5f)" % (err[i], tol[i], ref[i])
+    return float(err.max()) if ref.size else 0.0
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _mel_report():
+    yield
+    print("\n[mel parity] %d bins checked (%d at the 1e-5 floor, same bound), max |err| %.3e = %.4f of the tolerance"
+          % (MEL_STATS["bins"], MEL_STATS["at_floor"], MEL_STATS["max_err"], MEL_STATS["max_err_over_tol"]))
 
 
 # ------------------------------------------------------------------------------------ filter
@@ -88,6 +92,44 @@ def test_filter_edge_sizes(w_crnn):
     mel = eng.filter(big).cpu().numpy()
     for i in range(3):
         check_mel(mel[i], R.mel_stream(R.int16_to_float(big[i]), w_crnn))
+
+
+def _hdr_signals(n=8000):
+    """High-dynamic-range PCM: bands 60-120 dB below the frame's loudest bin but above the 1e-5 mel floor - the
+    cases an fp32 FFT gets wrong (round 1: 4.6e-4) and the reference's fp64 FFT does not."""
+    t = np.arange(n) / 16000.0
+    rng = np.random.default_rng(7)
+    sigs = [
+        1.4 * np.sin(2 * np.pi * 440.0 * t),                                               # clipping sine
+        0.999 * np.sin(2 * np.pi * 1000.0 * t),                                            # full-scale clean tone
+        0.9 * np.sin(2 * np.pi * 300.0 * t) + 2e-4 * np.sin(2 * np.pi * 5200.0 * t),       # tone + tone 73 dB down
+        0.95 * np.sin(2 * np.pi * 7000.0 * t) + 1e-3 * rng.standard_normal(n),             # HF tone over a -60 dB noise bed
+        0.5 * np.sign(np.sin(2 * np.pi * 125.0 * t)),                                      # square wave (1/k harmonics)
+        0.8 * np.sin(2 * np.pi * (200.0 + 3000.0 * t) * t),                                # chirp
+        0.6 + 0.0 * t,                                                                     # DC
+        np.where(np.arange(n) % 700 == 0, 0.99, 0.0) + 3e-4 * rng.standard_normal(n),      # clicks over a quiet bed
+    ]
+    return np.stack([np.round(np.clip(x, -1, 1) * 32767).astype(np.int16) for x in sigs])
+
+
+def test_filter_high_dynamic_range(w_crnn):
+    eng = get_engine("CRNN")
+    pcm = _hdr_signals()
+    mel = eng.filter(pcm).cpu().numpy()
+    worst = 0.0
+    for i in range(pcm.shape[0]):
+        worst = max(worst, check_mel(mel[i], R.mel_stream(R.int16_to_float(pcm[i]), w_crnn)))
+    print("high-dynamic-range set: max |err| %.3e" % worst)
+
+
+def test_filter_bench_shape_vs_oracle(w_crnn):
+    """The headline shape (512 streams x 10 s, 64-frame work items): first / middle / last streams against the oracle."""
+    eng = get_engine("CRNN")
+    pcm = synth.device_pcm(512, 160000, seed=1234, device=eng.device)
+    mel = eng.filter(pcm)
+    for sidx in (0, 1, 255, 510, 511):
+        ref = R.mel_stream(R.int16_to_float(pcm[sidx].cpu().numpy()), w_crnn)
+        check_mel(mel[sidx].cpu().numpy(), ref)
 
 
 def test_filter_mel_model_callable(w_crnn):

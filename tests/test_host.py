@@ -185,3 +185,36 @@ def test_tf_lite_opts_load_data_npz_and_metrics(tmp_path, capsys):
     assert r["recall"] == 2 / 3 and r["precision"] == 2 / 3 and abs(r["accuracy"] - 2 / 3) < 1e-12
     a = ETO.parse_args([])
     assert (a.tf_models_dir, a.testset, a.timesteps, a.num_features, a.model_type) == ("CRNN_tf_model", "test.h5", 151, 40, "CRNN")
+
+
+def test_fft64_header_matches_numpy(tmp_path):
+    """csrc/fft64.cuh (the fp64 FFT the K1 kernel runs) compiled for the CPU with its 16 lanes emulated in lock step
+    (tests/fft64_host.cpp) against np.fft.rfft: index algebra and accuracy of the exact device code, no GPU needed."""
+    import subprocess
+    exe = str(tmp_path / "fft64_host")
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-o", exe, os.path.join(ROOT, "tests", "fft64_host.cpp")])
+    rng = np.random.default_rng(0)
+    t = np.arange(512)
+    fr = (rng.standard_normal((6, 512)) * 0.1).astype(np.float32)
+    fr[1] = np.clip(np.round(32767 * 1.4 * np.sin(2 * np.pi * 440 / 16000 * t)) / 32767, -1, 1)
+    fr[2] = 0
+    fr[3] = (0.9 * np.sin(2 * np.pi * 300 / 16000 * t) + 2e-4 * np.sin(2 * np.pi * 5200 / 16000 * t)).astype(np.float32)
+    out = subprocess.run([exe], input=fr.tobytes(), capture_output=True, check=True).stdout
+    mag = np.frombuffer(out, np.float32).reshape(6, 257)
+    ref = np.abs(np.fft.rfft(fr * np.hanning(512), n=512)).astype(np.float32)
+    assert np.all(mag[2] == 0)
+    assert np.all(np.abs(mag - ref) <= 2e-7 * ref + 1e-30)
+
+
+def test_pcm_scaling_without_division_is_exact():
+    """filter.cu:pcm_to_float replaces s / 32767 by q0 = s*r, q = fma(fma(-q0, 32767, s), r, q0): equal to the IEEE
+    quotient numpy computes (wakeword/tflite.py:150) for all 65536 int16 values (fma emulated exactly in fp64: the
+    products have <= 48 significant bits and the sums cancel to few bits)."""
+    s = np.arange(-32768, 32768).astype(np.float32)
+    r = np.float32(3.0518509447574615e-05)
+    assert r == np.float32(1.0) / np.float32(32767.0)
+    q0 = (s * r).astype(np.float32)
+    rem = (s.astype(np.float64) - q0.astype(np.float64) * 32767.0).astype(np.float32)
+    assert np.all(rem.astype(np.float64) == s.astype(np.float64) - q0.astype(np.float64) * 32767.0)   # exact
+    q = (rem.astype(np.float64) * np.float64(r) + q0.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(q, s / np.float32(32767.0))

@@ -78,12 +78,13 @@ static std::vector<float> transposed(const float* src, int rows, int cols) {
 
 static int build_filter_tables(wwb_ctx* ctx, const wwb_weights* w) {
   const double PI = 3.14159265358979323846;
-  std::vector<float> hann(kFFT);
-  // np.hanning(512): 0.5 - 0.5 cos(2 pi n / 511); the 1/2 of the real-FFT split is folded in
-  for (int n = 0; n < kFFT; ++n) hann[n] = (float)(0.5 * (0.5 - 0.5 * cos(2.0 * PI * n / (kFFT - 1))));
-  std::vector<float2> t256(256), t512(257);
-  for (int k = 0; k < 256; ++k) t256[k] = make_float2((float)cos(2 * PI * k / 256), (float)-sin(2 * PI * k / 256));
-  for (int k = 0; k < 257; ++k) t512[k] = make_float2((float)cos(2 * PI * k / 512), (float)-sin(2 * PI * k / 512));
+  // fp64 tables of the FFT (fft64.cuh): np.hanning(512) = 0.5 - 0.5 cos(2 pi n / 511) with the 1/2 of the real-FFT
+  // split folded in; W256^k, W512^k
+  std::vector<double> hann(kFFT);
+  for (int n = 0; n < kFFT; ++n) hann[n] = 0.5 * (0.5 - 0.5 * cos(2.0 * PI * n / (kFFT - 1)));
+  std::vector<double2> t256(256), t512(256);
+  for (int k = 0; k < 256; ++k) t256[k] = make_double2(cos(2 * PI * k / 256), -sin(2 * PI * k / 256));
+  for (int k = 0; k < 256; ++k) t512[k] = make_double2(cos(2 * PI * k / 512), -sin(2 * PI * k / 512));
   int rc;
   if ((rc = upload(ctx, hann, &ctx->hann))) return rc;
   if ((rc = upload(ctx, t256, &ctx->tw256))) return rc;
@@ -95,16 +96,18 @@ static int build_filter_tables(wwb_ctx* ctx, const wwb_weights* w) {
   for (int m = 0; m < kMel; ++m) {
     band_seg0[m] = (int)seg_band.size();
     bias[m] = w->mel_b ? w->mel_b[m] : 0.f;
-    int in_seg = 0;
+    int in_seg = 0, last = -2;
     for (int k = 0; k < kBins; ++k) {
       float v = w->mel_w[(size_t)m * kBins + k];
       if (v == 0.f) continue;
-      if (in_seg == 0 || in_seg == kSegTaps) {
+      // a segment is a run of CONSECUTIVE bins (filter.cu reads it as seg_bin0 + t): a gap in the row starts a new one
+      if (in_seg == 0 || in_seg == kSegTaps || k != last + 1) {
         seg_band.push_back(m);
         seg_first.push_back((int)tap_bin.size());
         seg_count.push_back(0);
         in_seg = 0;
       }
+      last = k;
       tap_bin.push_back(k);
       tap_w.push_back(v);
       seg_count.back()++;

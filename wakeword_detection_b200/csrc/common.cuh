@@ -103,9 +103,9 @@ struct wwb_ctx {
   int sm_count = 148;
   float mel_floor = 1e-5f, mel_log_offset = 0.f, mel_scale = 0.5f;
   wwb::MelTables mel;
-  float* hann = nullptr;       // [512] fp32 (np.hanning rounded from fp64)
-  float2* tw256 = nullptr;     // [256] W256^k
-  float2* tw512 = nullptr;     // [257] W512^k
+  double* hann = nullptr;      // [512] 0.5 * np.hanning(512), fp64 (fft64.cuh)
+  double2* tw256 = nullptr;    // [256] W256^k
+  double2* tw512 = nullptr;    // [256] W512^k
   wwb::CrnnWeights crnn;
   wwb::WavenetWeights wn;
   wwb::StreamState st;

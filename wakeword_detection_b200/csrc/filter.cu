@@ -1,27 +1,28 @@
-// K1 — fused filter kernel: PCM -> (scale/clip) -> pre-emphasis -> frames of 512 @ hop 160
-// -> Hann -> 512-point real FFT -> |.| -> 257x40 mel (sparse) -> 0.5*(ln(max(.,1e-5))+11.5129).
+// K1 - fused filter kernel: PCM -> (scale/clip) -> pre-emphasis -> frames of 512 @ hop 160
+// -> Hann -> 512-point real FFT (fp64) -> |.| -> 257x40 mel (sparse) -> 0.5*(ln(max(.,1e-5))+11.5129).
 //
 // Replaces (reference): spokestack/wakeword/tflite.py:148-191, utils/tf_lite/filter.py:38-75
-// and filter.tflite.  HBM traffic is the algorithmic minimum (each PCM sample read once
-// per tile + 6 % halo, each mel value written once); the limiter is fp32 ALU work of the
-// FFT, so the layout is chosen for ALU efficiency:
-//   * 16 threads per frame; the 512 real samples are packed into 256 complex points,
-//     z[n] = x[2n] + i x[2n+1], and transformed as 16 x 16 (two in-register radix-16
-//     passes, one transpose through shared memory, twiddles W256^(j*k) held in registers
-//     because j is fixed per thread for the whole kernel);
-//   * the split step of the real FFT pairs bin k with 256-k; the partner value lives in
-//     lane (16-j) of the same 16-lane group and is fetched with one shuffle per value;
-//   * magnitudes go to shared memory, the mel projection is evaluated from a segment
-//     table (<= 8 non-zeros per segment, fixed summation order => deterministic results).
+// and filter.tflite.  HBM traffic is the algorithmic minimum (each PCM sample read once per chunk of a stream + 3 %
+// halo, each mel value written once); the limiter is the fp64 pipe (fft64.cuh explains why the FFT is fp64:
+// ~8900 fp64 instructions per frame against 64 per clock and SM), so the layout keeps that pipe fed:
+//   * every WARP is an independent pipeline over chunks of one stream, two frames at a time (one per 16-lane half);
+//     it owns its shared memory (sample ring, transpose buffers, magnitudes) and synchronises with __syncwarp only,
+//     so the warps of an SM drift apart and one warp's staging / mel phase overlaps another's butterflies;
+//   * window and twiddle factors a lane needs are the same for every frame (lane j is fixed): they live in
+//     registers (fft64.cuh LaneConsts), W512^k comes from shared memory (both halves read the same address);
+//   * consecutive frames overlap by 352 samples: an iteration stages only the 320 new samples of its frame pair
+//     into the warp's ring (int16 -> f32 exactly as the reference converts them), prefetched one iteration ahead;
+//   * magnitudes go to shared memory, the mel projection is evaluated from a segment table (<= 8 non-zeros per
+//     segment, fixed summation order => deterministic results, bit-identical to mel_from_mag_kernel).
 #include "common.cuh"
+#include "fft64.cuh"
 
 namespace wwb {
 
-constexpr int FR_TILE = 16;                                // frames per CTA pass
-constexpr int F_THREADS = FR_TILE * 16;                    // 256
-constexpr int TILE_SAMPLES = (FR_TILE - 1) * kHop + kFFT;  // 2912
-constexpr int XP = 17;                                     // transpose pitch (float2)
-constexpr int MAGP = 273;                                  // magnitude row pitch (floats)
+constexpr int F_WARPS = 12;                // independent warp pipelines per CTA (3 per scheduler; 16 KB of shared memory each)
+constexpr int F_THREADS = F_WARPS * 32;    // 384 (x 168 registers = one CTA per SM)
+constexpr int F_RING = 1024;               // floats per warp ring (>= 672 live samples + 320 staged ahead)
+constexpr int MAGP = 272;                  // magnitude entries per warp (257 bins + zeroed padding read by padded taps)
 constexpr int MAX_SEG = 128;
 
 struct MelParams {
@@ -31,121 +32,47 @@ struct MelParams {
 
 struct FilterParams {
   const void* pcm;
-  int dtype;
   int64_t n_streams, n_samples, pitch;
   int64_t n_frames;        // per stream
-  int tiles_per_stream;
-  int64_t n_tiles;
+  int item_frames;         // frames per work item (even)
+  int items_per_stream;
+  int64_t n_items;
   float a;                 // pre-emphasis
   float* mel;              // [S, F, 40]
-  const float* hann_half;  // [512] 0.5*hann
-  const float2* tw256;
-  const float2* tw512;
+  const double* hann_half; // [512] 0.5*np.hanning(512)
+  const double2* tw256;    // [256] W256^k
+  const double2* tw512;    // [256] W512^k
   MelParams mp;
 };
 
+struct __align__(16) FilterWarpSmem {
+  float ring[F_RING];
+  double2 xch[2][16 * f64::XP];
+  float2 mag[MAGP];          // [bin] = (frame of half 0, frame of half 1): one 8-byte load serves both frames
+  float2 partial[MAX_SEG];
+};
+
 struct __align__(16) FilterSmem {
-  float samples[TILE_SAMPLES + 8];
-  float2 xch[FR_TILE][16 * XP];
-  float mag[FR_TILE][MAGP];
-  float hann[kFFT];
-  float2 tw512[256];
-  float partial[FR_TILE][MAX_SEG];
-  // mel tables (batch kernel): segment -> taps, band -> segments
-  float seg_w[MAX_SEG][8];             // every segment padded to 8 taps (weight 0, bin 0): fma(0, x, acc) == acc
-  unsigned short seg_bin[MAX_SEG][8];
+  FilterWarpSmem w[F_WARPS];
+  double2 tw512[256];
+  double2 hann2[256];        // window of sample pair n (fft64.cuh)
+  double2 twj[256];          // W256^(j k2) at [16 j + k2]
+  // mel tables: a segment = up to 8 CONSECUTIVE bins of one band (the non-zeros of a mel band are contiguous), padded to 8
+  // taps with weight 0 (fma(0, x, acc) == acc: the padded taps read the following bins / the zeroed padding); band -> segments
+  float seg_w[MAX_SEG][8];
+  int seg_bin0[MAX_SEG];
   int band_seg0[kMel + 1];
   float band_bias[kMel];
 };
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-
-// forward radix-4 butterfly (W4 = -i), in place, natural output order
-__device__ __forceinline__ void bfly4(float2& a0, float2& a1, float2& a2, float2& a3) {
-  float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
-  a0 = cadd(s02, s13);
-  a2 = csub(s02, s13);
-  a1 = make_float2(d02.x + d13.y, d02.y - d13.x);
-  a3 = make_float2(d02.x - d13.y, d02.y + d13.x);
-}
-
-// in-register forward DFT of 16 points.  Input natural order; output X[k] is left in
-// v[4*(k&3) + (k>>2)]  (see XI()).
-__device__ __forceinline__ void fft16(float2 (&v)[16]) {
-  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R = 0.70710678118654752f;
-#pragma unroll
-  for (int a = 0; a < 4; ++a) bfly4(v[a], v[a + 4], v[a + 8], v[a + 12]);
-  // twiddles W16^(a*q) on v[a + 4q]
-  v[1 + 4] = cmul(v[1 + 4], make_float2(C1, -S1));                                   // W^1
-  v[1 + 8] = make_float2((v[1 + 8].x + v[1 + 8].y) * R, (v[1 + 8].y - v[1 + 8].x) * R);   // W^2
-  v[1 + 12] = cmul(v[1 + 12], make_float2(S1, -C1));                                 // W^3
-  v[2 + 4] = make_float2((v[2 + 4].x + v[2 + 4].y) * R, (v[2 + 4].y - v[2 + 4].x) * R);   // W^2
-  v[2 + 8] = make_float2(v[2 + 8].y, -v[2 + 8].x);                                   // W^4 = -i
-  v[2 + 12] = make_float2((v[2 + 12].y - v[2 + 12].x) * R, -(v[2 + 12].x + v[2 + 12].y) * R);  // W^6
-  v[3 + 4] = cmul(v[3 + 4], make_float2(S1, -C1));                                   // W^3
-  v[3 + 8] = make_float2((v[3 + 8].y - v[3 + 8].x) * R, -(v[3 + 8].x + v[3 + 8].y) * R);  // W^6
-  v[3 + 12] = cmul(v[3 + 12], make_float2(-C1, S1));                                 // W^9
-#pragma unroll
-  for (int q = 0; q < 4; ++q) bfly4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-}
-__device__ __forceinline__ constexpr int XI(int k) { return 4 * (k & 3) + (k >> 2); }
-
 __device__ __forceinline__ float pcm_to_float(int16_t s) {
   // frame.astype(np.float32) / (2**15 - 1), np.clip(-1, 1)   (wakeword/tflite.py:150-151)
-  float x = __fdiv_rn((float)s, 32767.0f);
+  // The correctly rounded quotient without the division subroutine: q0 = s*r, one FMA residual, one FMA correction
+  // (r = fl(1/32767)); equal to IEEE s/32767 for all 65536 inputs (checked exhaustively, tests/test_host.py).
+  const float r = 3.0518509447574615e-05f, f = (float)s;
+  const float q0 = __fmul_rn(f, r);
+  const float x = __fmaf_rn(__fmaf_rn(-q0, 32767.0f, f), r, q0);
   return fminf(fmaxf(x, -1.0f), 1.0f);
-}
-
-// One frame per 16-lane group: samples (already pre-emphasised) in shared memory at `x`
-// (8-byte aligned); writes 257 magnitudes to `mag`.
-__device__ __forceinline__ void frame_spectrum(const float* __restrict__ x, const float* __restrict__ hann,
-                                               const float2* __restrict__ tw512, const float2 (&twj)[16],
-                                               float2* __restrict__ xch, float* __restrict__ mag, int j,
-                                               unsigned group_mask) {
-  float2 v[16];
-  const float2* x2 = reinterpret_cast<const float2*>(x);
-  const float2* h2 = reinterpret_cast<const float2*>(hann);
-#pragma unroll
-  for (int m = 0; m < 16; ++m) {
-    float2 s = x2[j + 16 * m];
-    float2 h = h2[j + 16 * m];
-    v[m] = make_float2(s.x * h.x, s.y * h.y);
-  }
-  fft16(v);
-  // Y[k2] *= W256^(j*k2); transpose through shared memory
-  xch[j * XP + 0] = v[XI(0)];
-#pragma unroll
-  for (int k2 = 1; k2 < 16; ++k2) xch[j * XP + k2] = cmul(v[XI(k2)], twj[k2]);
-  __syncwarp(group_mask);
-#pragma unroll
-  for (int n1 = 0; n1 < 16; ++n1) v[n1] = xch[n1 * XP + j];
-  __syncwarp(group_mask);
-  fft16(v);
-  // Z[16*k1 + j] = v[XI(k1)].  Real-FFT split: X[k] = E + W512^k * O with
-  // E = (Zk + conj(Zp))/2, O = -i (Zk - conj(Zp))/2, Zp = Z[(256-k) mod 256]; the 1/2 is
-  // folded into the window table.
-  const int lane = threadIdx.x & 31;
-  const int src = (lane & 16) | ((16 - j) & 15);
-#pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) {
-    float2 zk = v[XI(k1)];
-    float2 send = v[XI(15 - k1)];
-    float2 zp;
-    zp.x = __shfl_sync(group_mask, send.x, src);
-    zp.y = __shfl_sync(group_mask, send.y, src);
-    if (j == 0) zp = v[XI((16 - k1) & 15)];
-    float er = zk.x + zp.x, ei = zk.y - zp.y;
-    float orr = zk.y + zp.y, oi = zp.x - zk.x;
-    float2 w = tw512[16 * k1 + j];
-    float xr = er + w.x * orr - w.y * oi;
-    float xi = ei + w.x * oi + w.y * orr;
-    mag[16 * k1 + j] = sqrtf(xr * xr + xi * xi);
-    if (j == 0 && k1 == 0) mag[256] = fabsf(zk.x - zk.y);   // W512^256 = -1
-  }
 }
 
 template <typename T>
@@ -159,175 +86,203 @@ __device__ __forceinline__ float load_sample<float>(const float* p, int64_t i) {
   return __ldg(p + i);
 }
 
-// mel projection + log compression for `nf` frames whose magnitudes are in sm.mag;
-// writes out[frame*40 + band].
-__device__ __forceinline__ void mel_phase(FilterSmem& sm, const MelParams& P, int nf, float* __restrict__ out) {
-  const MelTables& mt = P.mt;
-  const int n_items = mt.n_seg * FR_TILE;
-  for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
-    int f = it & (FR_TILE - 1), seg = it / FR_TILE;
-    if (f < nf) {
-      int first = __ldg(mt.seg_first + seg), cnt = __ldg(mt.seg_count + seg);
-      float acc = 0.f;
-      for (int t = 0; t < cnt; ++t)
-        acc = fmaf(__ldg(mt.tap_w + first + t), sm.mag[f][__ldg(mt.tap_bin + first + t)], acc);
-      sm.partial[f][seg] = acc;
-    }
+__device__ __forceinline__ void load_tables(FilterSmem& sm, const double* __restrict__ hann_half, const double2* __restrict__ tw256,
+                                            const double2* __restrict__ tw512, const MelTables& mt, int tid, int nthreads) {
+  for (int i = tid; i < 256; i += nthreads) {
+    sm.tw512[i] = tw512[i];
+    sm.hann2[i] = make_double2(hann_half[2 * i], hann_half[2 * i + 1]);
+    sm.twj[i] = tw256[((i >> 4) * (i & 15)) & 255];
   }
-  __syncthreads();
-  for (int o = threadIdx.x; o < nf * kMel; o += blockDim.x) {
-    int f = o / kMel, band = o - f * kMel;
-    int s0 = __ldg(mt.band_seg0 + band), s1 = __ldg(mt.band_seg0 + band + 1);
-    float acc = 0.f;
-    for (int s = s0; s < s1; ++s) acc += sm.partial[f][s];
-    acc += __ldg(mt.bias + band);
-    acc = fmaxf(acc, P.mel_floor);
-    float y = logf(acc);
-    y = __fsub_rn(y, P.mel_log_offset);
-    out[o] = __fmul_rn(y, P.mel_scale);
+  for (int i = tid; i < mt.n_seg * 8; i += nthreads) {
+    const int seg = i >> 3, t = i & 7;
+    sm.seg_w[seg][t] = t < mt.seg_count[seg] ? mt.tap_w[mt.seg_first[seg] + t] : 0.0f;
+    if (t == 0) sm.seg_bin0[seg] = mt.tap_bin[mt.seg_first[seg]];
+  }
+  for (int i = tid; i <= kMel; i += nthreads) sm.band_seg0[i] = mt.band_seg0[i];
+  for (int i = tid; i < kMel; i += nthreads) sm.band_bias[i] = mt.bias[i];
+  for (int w = 0; w < F_WARPS; ++w)
+    for (int i = tid; i < MAGP; i += nthreads) sm.w[w].mag[i] = make_float2(0.f, 0.f);
+}
+
+// One frame per 16-lane half of the warp (both halves execute this together): samples from `load` (pair m of lane j =
+// samples 2(j+16m), +1 of the frame) -> 257 magnitudes in mag[bin].x (half 0) / .y (half 1).  Contains two __syncwarp.
+template <typename LoadFn>
+__device__ __forceinline__ void frame_spectrum64(LoadFn load, const FilterSmem& sm, double2* __restrict__ xch,
+                                                 float2* __restrict__ mag2, int lane) {
+  const int j = lane & 15, h = lane >> 4;
+  f64::pass1(load, sm.hann2, sm.twj, xch, j);
+  __syncwarp();
+  double2 v[16];
+  f64::pass2(xch, j, v);
+  __syncwarp();
+  float* mag = reinterpret_cast<float*>(mag2) + h;   // this half's component, stride 2
+  const int src = (lane & 16) | ((16 - j) & 15);
+  // lane j handles the bin pairs (k, 256 - k), k = 16 k1 + j, k1 = 0..7; Z[256-k] is v[XI(15-k1)] of lane 16-j
+  // (lane 0 pairs with itself: Z[16 (16-k1)], and Z[256] = Z[0])
+#pragma unroll
+  for (int k1 = 0; k1 < 8; ++k1) {
+    const double2 up = v[f64::XI(15 - k1)], self = v[f64::XI(k1 == 0 ? 0 : 16 - k1)];
+    const double sx = j == 0 ? self.x : up.x, sy = j == 0 ? self.y : up.y;
+    const double2 zp = make_double2(__shfl_sync(0xffffffffu, sx, src), __shfl_sync(0xffffffffu, sy, src));
+    float mk, mnk;
+    f64::split_pair(v[f64::XI(k1)], zp, sm.tw512[16 * k1 + j], mk, mnk);
+    mag[2 * (16 * k1 + j)] = mk;
+    mag[2 * (256 - 16 * k1 - j)] = mnk;
+  }
+  if (j == 0) {   // bin 128 pairs with itself
+    float mk, mnk;
+    f64::split_pair(v[f64::XI(8)], v[f64::XI(8)], sm.tw512[128], mk, mnk);
+    mag[2 * 128] = mk;
   }
 }
 
-// Same arithmetic as mel_phase (per segment an fma chain from 0, segments added in order, bias, floor, log), i.e.
-// bit-identical to mel_phase / mel_from_mag_kernel, but with the tables in shared memory and every segment padded
-// to exactly 8 taps, so the 8 (weight, bin, magnitude) loads of an item are issued together instead of one
-// dependent load chain per tap.  Contains one barrier.
-__device__ __forceinline__ void mel_fast(FilterSmem& sm, const MelParams& P, int n_seg, int nf, float* __restrict__ out) {
-  for (int it = threadIdx.x; it < n_seg * FR_TILE; it += blockDim.x) {
-    const int f = it & (FR_TILE - 1), seg = it / FR_TILE;
-    if (f < nf) {
-      const float4 w0 = *reinterpret_cast<const float4*>(&sm.seg_w[seg][0]), w1 = *reinterpret_cast<const float4*>(&sm.seg_w[seg][4]);
-      const uint4 bb = *reinterpret_cast<const uint4*>(&sm.seg_bin[seg][0]);
-      const float* row = sm.mag[f];
-      const float m0 = row[bb.x & 0xffff], m1 = row[bb.x >> 16], m2 = row[bb.y & 0xffff], m3 = row[bb.y >> 16];
-      const float m4 = row[bb.z & 0xffff], m5 = row[bb.z >> 16], m6 = row[bb.w & 0xffff], m7 = row[bb.w >> 16];
-      float acc = 0.f;
-      acc = fmaf(w0.x, m0, acc); acc = fmaf(w0.y, m1, acc); acc = fmaf(w0.z, m2, acc); acc = fmaf(w0.w, m3, acc);
-      acc = fmaf(w1.x, m4, acc); acc = fmaf(w1.y, m5, acc); acc = fmaf(w1.z, m6, acc); acc = fmaf(w1.w, m7, acc);
-      sm.partial[f][seg] = acc;
-    }
+__device__ __forceinline__ float mel_log(float acc, float bias, const MelParams& P) {
+  acc += bias;
+  acc = fmaxf(acc, P.mel_floor);
+  return __fmul_rn(__fsub_rn(logf(acc), P.mel_log_offset), P.mel_scale);
+}
+
+// mel projection + log compression of the two frames of a warp whose magnitudes are in ws.mag.  Per segment an fma chain
+// from 0, segments added in order, bias, floor, log: bit-identical to mel_from_mag_kernel.  The band sums of frame 0 / 1
+// go to out0 / out1 (nullptr = frame not wanted).  Contains two __syncwarp.
+__device__ __forceinline__ void mel_pair(const FilterSmem& sm, FilterWarpSmem& ws, const MelParams& P, int n_seg,
+                                         float* __restrict__ out0, float* __restrict__ out1, int lane) {
+  __syncwarp();
+  for (int seg = lane; seg < n_seg; seg += 32) {
+    const float4 w0 = *reinterpret_cast<const float4*>(&sm.seg_w[seg][0]), w1 = *reinterpret_cast<const float4*>(&sm.seg_w[seg][4]);
+    const float2* m = ws.mag + sm.seg_bin0[seg];
+    const float2 m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5], m6 = m[6], m7 = m[7];
+    float a0 = 0.f, a1 = 0.f;
+    a0 = fmaf(w0.x, m0.x, a0); a1 = fmaf(w0.x, m0.y, a1);
+    a0 = fmaf(w0.y, m1.x, a0); a1 = fmaf(w0.y, m1.y, a1);
+    a0 = fmaf(w0.z, m2.x, a0); a1 = fmaf(w0.z, m2.y, a1);
+    a0 = fmaf(w0.w, m3.x, a0); a1 = fmaf(w0.w, m3.y, a1);
+    a0 = fmaf(w1.x, m4.x, a0); a1 = fmaf(w1.x, m4.y, a1);
+    a0 = fmaf(w1.y, m5.x, a0); a1 = fmaf(w1.y, m5.y, a1);
+    a0 = fmaf(w1.z, m6.x, a0); a1 = fmaf(w1.z, m6.y, a1);
+    a0 = fmaf(w1.w, m7.x, a0); a1 = fmaf(w1.w, m7.y, a1);
+    ws.partial[seg] = make_float2(a0, a1);
   }
-  __syncthreads();
-  for (int o = threadIdx.x; o < nf * kMel; o += blockDim.x) {
-    const int f = o / kMel, band = o - f * kMel;
+  __syncwarp();
+  {   // bands 0..31: one lane each, both frames
+    const int s0 = sm.band_seg0[lane], s1 = sm.band_seg0[lane + 1];
+    float a0 = 0.f, a1 = 0.f;
+    for (int s = s0; s < s1; ++s) {
+      const float2 p = ws.partial[s];
+      a0 += p.x; a1 += p.y;
+    }
+    const float bias = sm.band_bias[lane];
+    if (out0) out0[lane] = mel_log(a0, bias, P);
+    if (out1) out1[lane] = mel_log(a1, bias, P);
+  }
+  if (lane < 2 * (kMel - 32)) {   // bands 32..39: lanes 0..7 frame 0, lanes 8..15 frame 1
+    const int band = 32 + (lane & 7), f = lane >> 3;
     const int s0 = sm.band_seg0[band], s1 = sm.band_seg0[band + 1];
-    float acc = 0.f;
-    for (int s = s0; s < s1; ++s) acc += sm.partial[f][s];
-    acc += sm.band_bias[band];
-    acc = fmaxf(acc, P.mel_floor);
-    float y = logf(acc);
-    y = __fsub_rn(y, P.mel_log_offset);
-    out[o] = __fmul_rn(y, P.mel_scale);
+    float a = 0.f;
+    for (int s = s0; s < s1; ++s) {
+      const float2 p = ws.partial[s];
+      a += f ? p.y : p.x;
+    }
+    float* out = f ? out1 : out0;
+    if (out) out[band] = mel_log(a, sm.band_bias[band], P);
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(F_THREADS, 2) filter_kernel(const FilterParams P) {
+__global__ void __launch_bounds__(F_THREADS, 1) filter_kernel(const FilterParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FilterSmem& sm = *reinterpret_cast<FilterSmem*>(smem_raw);
-  const int tid = threadIdx.x;
-  const int j = tid & 15;          // lane within the frame group
-  const int g = tid >> 4;          // frame within the tile
-  const unsigned group_mask = (tid & 16) ? 0xffff0000u : 0x0000ffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = lane & 15, h = lane >> 4;
+  FilterWarpSmem& ws = sm.w[warp];
 
-  for (int i = tid; i < kFFT; i += F_THREADS) sm.hann[i] = P.hann_half[i];
-  for (int i = tid; i < 256; i += F_THREADS) sm.tw512[i] = P.tw512[i];
-  float2 twj[16];
-#pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) twj[k2] = P.tw256[(j * k2) & 255];
+  load_tables(sm, P.hann_half, P.tw256, P.tw512, P.mp.mt, tid, F_THREADS);
   __syncthreads();
-
-  {
-    const MelTables& mt = P.mp.mt;
-    for (int i = tid; i < mt.n_seg * 8; i += F_THREADS) {
-      const int seg = i >> 3, t = i & 7;
-      const bool in = t < mt.seg_count[seg];
-      sm.seg_w[seg][t] = in ? mt.tap_w[mt.seg_first[seg] + t] : 0.0f;
-      sm.seg_bin[seg][t] = in ? (unsigned short)mt.tap_bin[mt.seg_first[seg] + t] : (unsigned short)0;
-    }
-    for (int i = tid; i <= kMel; i += F_THREADS) sm.band_seg0[i] = mt.band_seg0[i];
-    for (int i = tid; i < kMel; i += F_THREADS) sm.band_bias[i] = mt.bias[i];
-  }
-  __syncthreads();
+  const int n_seg = P.mp.mt.n_seg;
 
   const T* pcm = reinterpret_cast<const T*>(P.pcm);
-  // Fast path (int16, 8-byte aligned rows, no pre-emphasis = the reference's default): the next tile's PCM is
-  // prefetched into registers while the current tile's spectra are computed, and a tile costs two barriers.
-  const bool fast = sizeof(T) == 2 && P.a == 0.0f && (reinterpret_cast<uintptr_t>(pcm) & 7) == 0 && (P.pitch & 3) == 0;
-  constexpr int NPRE = (TILE_SAMPLES / 4 + F_THREADS - 1) / F_THREADS;   // 3 uint2 per thread
-  uint2 pre[NPRE];
-  auto tile_geom = [&](int64_t tile, int64_t& s_out, int64_t& f0_out, int& nf_out) {
-    s_out = tile / P.tiles_per_stream;
-    f0_out = (tile - s_out * P.tiles_per_stream) * FR_TILE;
-    nf_out = (int)min((int64_t)FR_TILE, P.n_frames - f0_out);
-  };
-  auto prefetch = [&](int64_t tile) {
-    int64_t s, f0; int nf;
-    tile_geom(tile, s, f0, nf);
-    const int ns = (nf - 1) * kHop + kFFT;
-    const uint2* v4 = reinterpret_cast<const uint2*>(reinterpret_cast<const int16_t*>(P.pcm) + s * P.pitch + f0 * kHop);
-#pragma unroll
-    for (int c = 0; c < NPRE; ++c) {
-      const int i = tid + c * F_THREADS;
-      pre[c] = (i < ns / 4) ? __ldg(v4 + i) : make_uint2(0u, 0u);
-    }
-  };
-  if (fast && (int64_t)blockIdx.x < P.n_tiles) prefetch(blockIdx.x);
+  // Fast path (int16, 4-byte aligned rows of even length, no pre-emphasis = the reference's default): 32-bit loads of
+  // sample pairs, the next iteration's 320 samples prefetched into registers behind the butterflies.
+  const bool fast = sizeof(T) == 2 && P.a == 0.0f && (reinterpret_cast<uintptr_t>(pcm) & 3) == 0 && (P.pitch & 1) == 0 &&
+                    (P.n_samples & 1) == 0;
 
-  for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-    int64_t s, f0; int nf;
-    tile_geom(tile, s, f0, nf);
-    const int ns = (nf - 1) * kHop + kFFT;
+  for (int64_t item = (int64_t)blockIdx.x * F_WARPS + warp; item < P.n_items; item += (int64_t)gridDim.x * F_WARPS) {
+    const int64_t s = item / P.items_per_stream;
+    const int64_t f0 = (item - s * P.items_per_stream) * P.item_frames;
+    const int nf = (int)min((int64_t)P.item_frames, P.n_frames - f0);
     const T* row = pcm + s * P.pitch;
-    const int64_t start = f0 * kHop;
+    const int64_t base = f0 * kHop;              // stream sample at ring position 0
+    const int64_t n_avail = P.n_samples - base;  // samples of the stream from `base` on
 
-    // stage samples (converted to float) in shared memory
+    // stage relative samples [r0, r0 + cnt) into the ring (cnt even, r0 even); generic path
+    auto stage_generic = [&](int r0, int cnt) {
+      for (int r = lane; r < cnt; r += 32) {
+        const int64_t idx = base + r0 + r;
+        float v = 0.f;
+        if (idx < P.n_samples) {
+          v = load_sample<T>(row, idx);
+          if (P.a != 0.0f) {
+            // y[n] = x[n] - a*x[n-1] with fp32 product and difference (numpy semantics after the first call)
+            const float xp = idx > 0 ? load_sample<T>(row, idx - 1) : 0.0f;
+            v = __fsub_rn(v, __fmul_rn(P.a, xp));
+          }
+        }
+        ws.ring[(r0 + r) & (F_RING - 1)] = v;
+      }
+    };
+    const uint32_t* row32 = reinterpret_cast<const uint32_t*>(row + base);   // (fast path only)
+    auto stage_word = [&](int r0, int wi, uint32_t word) {   // word wi of the range that starts at relative sample r0
+      *reinterpret_cast<float2*>(&ws.ring[(r0 + 2 * wi) & (F_RING - 1)]) =
+          make_float2(pcm_to_float((int16_t)(word & 0xffff)), pcm_to_float((int16_t)(word >> 16)));
+    };
+    uint32_t pre[5];
+    auto prefetch = [&](int r0) {   // 320 samples = 160 words from relative sample r0
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        const int wi = lane + 32 * c;
+        pre[c] = (r0 + 2 * wi < n_avail) ? __ldg(row32 + (r0 >> 1) + wi) : 0u;
+      }
+    };
+
+    __syncwarp();   // the previous item's last reads of the ring are done
     if (fast) {
 #pragma unroll
-      for (int c = 0; c < NPRE; ++c) {
-        const int i = tid + c * F_THREADS;
-        if (i < ns / 4) {
-          const uint2 r = pre[c];
-          *reinterpret_cast<float4*>(&sm.samples[4 * i]) =
-              make_float4(pcm_to_float((int16_t)(r.x & 0xffff)), pcm_to_float((int16_t)(r.x >> 16)),
-                          pcm_to_float((int16_t)(r.y & 0xffff)), pcm_to_float((int16_t)(r.y >> 16)));
-        }
+      for (int c = 0; c < 6; ++c) {   // first 352 samples = 176 words
+        const int wi = lane + 32 * c;
+        if (wi < 176) stage_word(0, wi, (2 * wi < n_avail) ? __ldg(row32 + wi) : 0u);
       }
-    } else if (sizeof(T) == 2 && ((reinterpret_cast<uintptr_t>(row + start) & 7) == 0)) {
-      const uint2* v4 = reinterpret_cast<const uint2*>(row + start);
-      for (int i = tid; i < ns / 4; i += F_THREADS) {
-        uint2 r = __ldg(v4 + i);
-        sm.samples[4 * i + 0] = pcm_to_float((int16_t)(r.x & 0xffff));
-        sm.samples[4 * i + 1] = pcm_to_float((int16_t)(r.x >> 16));
-        sm.samples[4 * i + 2] = pcm_to_float((int16_t)(r.y & 0xffff));
-        sm.samples[4 * i + 3] = pcm_to_float((int16_t)(r.y >> 16));
-      }
+      prefetch(352);
     } else {
-      for (int i = tid; i < ns; i += F_THREADS) sm.samples[i] = load_sample<T>(row, start + i);
+      stage_generic(0, 352);
     }
-    if (P.a != 0.0f) {
-      // y[n] = x[n] - a*x[n-1] with fp32 product and difference (numpy semantics)
-      __syncthreads();
-      float y[(TILE_SAMPLES + F_THREADS - 1) / F_THREADS];
-      int c = 0;
-      for (int i = tid; i < ns; i += F_THREADS, ++c) {
-        float xp = (i > 0) ? sm.samples[i - 1] : (start > 0 ? load_sample<T>(row, start - 1) : 0.0f);
-        y[c] = __fsub_rn(sm.samples[i], __fmul_rn(P.a, xp));
-      }
-      __syncthreads();
-      c = 0;
-      for (int i = tid; i < ns; i += F_THREADS, ++c) sm.samples[i] = y[c];
-    }
-    __syncthreads();
-    if (fast && tile + gridDim.x < P.n_tiles) prefetch(tile + gridDim.x);   // latency hidden behind the FFTs
 
-    if (g < nf)
-      frame_spectrum(sm.samples + g * kHop, sm.hann, sm.tw512, twj, sm.xch[g], sm.mag[g], j, group_mask);
-    __syncthreads();
-    // (no barrier after this: the next store goes to `samples`, which nobody reads any more, and the next
-    //  spectra overwrite `mag` / the next mel phase `partial` only after the barrier that follows that store)
-    mel_fast(sm, P.mp, P.mp.mt.n_seg, nf, P.mel + (s * P.n_frames + f0) * kMel);
+    for (int i = 0; i < nf; i += 2) {
+      // new samples of this frame pair: relative [160 i + 352, 160 i + 672)
+      if (fast) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) stage_word(160 * i + 352, lane + 32 * c, pre[c]);
+      } else {
+        stage_generic(160 * i + 352, 320);
+      }
+      __syncwarp();
+      if (fast && i + 2 < nf) prefetch(160 * (i + 2) + 352);   // latency hidden behind the FFTs
+      const int rb = 160 * (i + h) + 2 * j;
+      auto load = [&](int m) {
+        const float2 x = *reinterpret_cast<const float2*>(&ws.ring[(rb + 32 * m) & (F_RING - 1)]);
+        return make_double2((double)x.x, (double)x.y);
+      };
+      frame_spectrum64(load, sm, ws.xch[h], ws.mag, lane);
+      float* out = P.mel + ((s * P.n_frames + f0 + i) * kMel);
+      mel_pair(sm, ws, P.mp, n_seg, out, i + 1 < nf ? out + kMel : nullptr, lane);
+    }
   }
+}
+
+static MelParams mel_params(const wwb_ctx* ctx) {
+  MelParams mp;
+  mp.mt = ctx->mel;
+  mp.mel_floor = ctx->mel_floor; mp.mel_log_offset = ctx->mel_log_offset; mp.mel_scale = ctx->mel_scale;
+  return mp;
 }
 
 int launch_filter(wwb_ctx* ctx, const void* pcm, int dtype, int64_t S, int64_t N, int64_t pitch,
@@ -338,15 +293,19 @@ int launch_filter(wwb_ctx* ctx, const void* pcm, int dtype, int64_t S, int64_t N
   if (S == 0 || F == 0) return WWB_OK;
   if (ctx->mel.n_seg > MAX_SEG) return fail(ctx, WWB_ERR_ARG, "mel matrix has too many segments");
   FilterParams P;
-  P.pcm = pcm; P.dtype = dtype; P.n_streams = S; P.n_samples = N; P.pitch = pitch;
+  P.pcm = pcm; P.n_streams = S; P.n_samples = N; P.pitch = pitch;
   P.n_frames = F;
-  P.tiles_per_stream = (int)((F + FR_TILE - 1) / FR_TILE);
-  P.n_tiles = S * P.tiles_per_stream;
+  // work items = chunks of a stream; 64 frames per item (352 / (64 * 160) = 3.4 % halo) unless that leaves warps idle
+  const int64_t n_warps = (int64_t)ctx->sm_count * F_WARPS;
+  int item_frames = 64;
+  while (item_frames > 2 && S * ((F + item_frames - 1) / item_frames) < 4 * n_warps) item_frames /= 2;
+  P.item_frames = item_frames;
+  P.items_per_stream = (int)((F + item_frames - 1) / item_frames);
+  P.n_items = S * P.items_per_stream;
   P.a = a; P.mel = mel; P.hann_half = ctx->hann; P.tw256 = ctx->tw256; P.tw512 = ctx->tw512;
-  P.mp.mt = ctx->mel;
-  P.mp.mel_floor = ctx->mel_floor; P.mp.mel_log_offset = ctx->mel_log_offset; P.mp.mel_scale = ctx->mel_scale;
+  P.mp = mel_params(ctx);
   size_t smem = sizeof(FilterSmem);
-  int64_t grid = std::min<int64_t>(P.n_tiles, (int64_t)ctx->sm_count * 2);
+  int64_t grid = std::min<int64_t>((P.n_items + F_WARPS - 1) / F_WARPS, (int64_t)ctx->sm_count);
   if (dtype == WWB_PCM_I16) {
     WWB_CUDA(ctx, cudaFuncSetAttribute(filter_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     filter_kernel<int16_t><<<(unsigned)grid, F_THREADS, smem, st>>>(P);
@@ -359,125 +318,148 @@ int launch_filter(wwb_ctx* ctx, const void* pcm, int dtype, int64_t S, int64_t N
 }
 
 // ---------------------------------------------------------------------------------------
-// Streaming front end (WakewordTrigger._sample, wakeword/tflite.py:148-168) for many
-// streams: one CTA per stream appends the chunk to the stream's pending samples, emits
-// every frame that completes (only analysed while is_speech, :166-167), pushes the mel
-// frames into the stream's ring and records one encoder window per analysed frame.
+// Streaming front end (WakewordTrigger._sample, wakeword/tflite.py:148-168) for many streams, three small kernels:
+//   plan   (one thread per stream)  how many frames the chunk completes; if they are analysed (is_speech, :166-167)
+//          one encoder window per frame is recorded (win_stream / win_start) and the stream's slot reserved
+//   frames (one 16-lane half-warp per (stream, frame))  pending samples + chunk -> frame -> fp64 FFT -> mel row pushed
+//          into the stream's ring; with one new frame per stream and push (hop 1, BASELINE config 4) 16 streams share a
+//          CTA instead of one CTA per stream
+//   tail   (one CTA per stream)  unread PCM tail, previous sample, ring head
 struct StreamFilterParams {
   const int16_t* pcm;
   int64_t n;
+  int64_t n_streams;
   const uint8_t* is_speech;
   const uint8_t* is_active;
   float a;
   StreamState st;
   int L;
-  const float* hann_half;
-  const float2* tw256;
-  const float2* tw512;
+  const double* hann_half;
+  const double2* tw256;
+  const double2* tw512;
   MelParams mp;
 };
 
-__global__ void __launch_bounds__(F_THREADS, 2) stream_filter_kernel(const StreamFilterParams P) {
+__device__ __forceinline__ int stream_total_frames(int total) { return total >= kFFT ? (total - kFFT) / kHop + 1 : 0; }
+
+__global__ void __launch_bounds__(128) stream_plan_kernel(const StreamFilterParams P) {
+  const StreamState& S = P.st;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.n_streams) return;
+  int n_new = 0;
+  const bool active = P.is_active && P.is_active[s];   // "if not context.is_active: self._sample(...)" (:139-140)
+  const bool speech = P.is_speech ? (P.is_speech[s] != 0) : true;
+  if (!active && speech) {
+    const int n_frames = stream_total_frames(S.n_pending[s] + (int)P.n);
+    if (n_frames > 0) {
+      const int head = S.ring_head[s];
+      const int slot = atomicAdd(S.n_win, n_frames);
+      for (int q = 0; q < n_frames; ++q) {
+        S.win_stream[slot + q] = (int32_t)s;
+        S.win_start[slot + q] = (head + 1 + q) % S.ring;
+      }
+      S.win_slot[s] = slot;
+      n_new = n_frames;
+    }
+  }
+  S.n_new[s] = n_new;
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1) stream_frames_kernel(const StreamFilterParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FilterSmem& sm = *reinterpret_cast<FilterSmem*>(smem_raw);
-  __shared__ float mel_out[FR_TILE * kMel];
-  const int tid = threadIdx.x, j = tid & 15, g = tid >> 4;
-  const unsigned group_mask = (tid & 16) ? 0xffff0000u : 0x0000ffffu;
-  const int64_t s = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = lane & 15, h = lane >> 4;
+  FilterWarpSmem& ws = sm.w[warp];
   const StreamState& S = P.st;
 
-  for (int i = tid; i < kFFT; i += F_THREADS) sm.hann[i] = P.hann_half[i];
-  for (int i = tid; i < 256; i += F_THREADS) sm.tw512[i] = P.tw512[i];
-  float2 twj[16];
-#pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) twj[k2] = P.tw256[(j * k2) & 255];
+  load_tables(sm, P.hann_half, P.tw256, P.tw512, P.mp.mt, tid, F_THREADS);
+  __syncthreads();
+  const int n_seg = P.mp.mt.n_seg;
+  const int64_t n_items = P.n_streams * S.max_frames;
 
-  if (tid == 0) S.n_new[s] = 0;
-  if (P.is_active && P.is_active[s]) return;   // "if not context.is_active: self._sample(...)" (:139-140)
+  // a warp takes two items (stream, frame) per iteration, one per half
+  for (int64_t it0 = ((int64_t)blockIdx.x * F_WARPS + warp) * 2; it0 < n_items; it0 += (int64_t)gridDim.x * F_WARPS * 2) {
+    const int64_t it = it0 + h;
+    const int64_t s = it < n_items ? it / S.max_frames : 0;
+    const int q = (int)(it - s * S.max_frames);
+    const bool live = it < n_items && q < S.n_new[s];
+    float* frame = ws.ring + h * kFFT;   // the ring doubles as two frame buffers
+    __syncwarp();
+    if (live) {
+      const int np = S.n_pending[s];
+      const float* pend = S.pending + s * S.pend_cap;
+      const int16_t* chunk = P.pcm + s * P.n;
+      const float prev = S.prev_sample[s];
+      for (int i = j; i < kFFT; i += 16) {
+        const int p = q * kHop + i;
+        float v;
+        if (p < np) {
+          v = pend[p];   // already pre-emphasised
+        } else {
+          const int c = p - np;
+          const float x = pcm_to_float(chunk[c]);
+          const float xp = c > 0 ? pcm_to_float(chunk[c - 1]) : prev;
+          v = (P.a != 0.0f) ? __fsub_rn(x, __fmul_rn(P.a, xp)) : x;
+        }
+        frame[i] = v;
+      }
+    }
+    __syncwarp();
+    auto load = [&](int m) {
+      const float2 x = *reinterpret_cast<const float2*>(&frame[2 * (j + 16 * m)]);
+      return make_double2((double)x.x, (double)x.y);
+    };
+    frame_spectrum64(load, sm, ws.xch[h], ws.mag, lane);
+    // the two halves are different streams: each frame goes to its own stream's ring row; the window for new frame q
+    // ends at ring row (head + L + q) % ring
+    const bool live0 = __shfl_sync(0xffffffffu, live ? 1 : 0, 0) != 0, live1 = __shfl_sync(0xffffffffu, live ? 1 : 0, 16) != 0;
+    const int64_t s0 = __shfl_sync(0xffffffffu, s, 0), s1 = __shfl_sync(0xffffffffu, s, 16);
+    const int q0 = __shfl_sync(0xffffffffu, q, 0), q1 = __shfl_sync(0xffffffffu, q, 16);
+    float* dst0 = live0 ? S.mel_ring + (s0 * S.ring + (S.ring_head[s0] + P.L + q0) % S.ring) * kMel : nullptr;
+    float* dst1 = live1 ? S.mel_ring + (s1 * S.ring + (S.ring_head[s1] + P.L + q1) % S.ring) * kMel : nullptr;
+    mel_pair(sm, ws, P.mp, n_seg, dst0, dst1, lane);
+  }
+}
 
+__global__ void __launch_bounds__(128) stream_tail_kernel(const StreamFilterParams P) {
+  const StreamState& S = P.st;
+  const int64_t s = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (P.is_active && P.is_active[s]) return;
   const int np = S.n_pending[s];
   const int total = np + (int)P.n;
+  const int n_frames = stream_total_frames(total);
   float* pend = S.pending + s * S.pend_cap;
-  // pending (already pre-emphasised) + new chunk -> shared memory, processed FR_TILE frames at a time
-  const bool speech = P.is_speech ? (P.is_speech[s] != 0) : true;
-  const int n_frames = total >= kFFT ? (total - kFFT) / kHop + 1 : 0;
   const float prev = S.prev_sample[s];
   const int16_t* chunk = P.pcm + s * P.n;
-  __syncthreads();
-
-  int head = S.ring_head[s];
-  for (int f0 = 0; f0 < n_frames; f0 += FR_TILE) {
-    const int nf = min(FR_TILE, n_frames - f0);
-    const int ns = (nf - 1) * kHop + kFFT;
-    const int base = f0 * kHop;
-    for (int i = tid; i < ns; i += F_THREADS) {
-      int p = base + i;
-      float v;
-      if (p < np) {
-        v = pend[p];
-      } else {
-        int c = p - np;
-        float x = pcm_to_float(chunk[c]);
-        float xp = c > 0 ? pcm_to_float(chunk[c - 1]) : prev;
-        v = (P.a != 0.0f) ? __fsub_rn(x, __fmul_rn(P.a, xp)) : x;
-      }
-      sm.samples[i] = v;
-    }
-    __syncthreads();
-    if (speech) {
-      if (g < nf)
-        frame_spectrum(sm.samples + g * kHop, sm.hann, sm.tw512, twj, sm.xch[g], sm.mag[g], j, group_mask);
-      __syncthreads();
-      mel_phase(sm, P.mp, nf, mel_out);
-      __syncthreads();
-      // push into the ring: the window for new frame q ends at ring row (head + L + q) % ring
-      for (int o = tid; o < nf * kMel; o += F_THREADS) {
-        int q = o / kMel, band = o - q * kMel;
-        int r = (head + P.L + f0 + q) % S.ring;
-        S.mel_ring[(s * S.ring + r) * kMel + band] = mel_out[o];
-      }
-    }
-    __syncthreads();
-  }
-  // bookkeeping by one thread: windows to evaluate, ring head, pending tail
-  if (speech && tid == 0 && n_frames > 0) {
-    int slot = atomicAdd(S.n_win, n_frames);
-    for (int q = 0; q < n_frames; ++q) {
-      S.win_stream[slot + q] = (int32_t)s;
-      S.win_start[slot + q] = (head + 1 + q) % S.ring;
-    }
-    S.n_new[s] = n_frames;
-    S.win_slot[s] = slot;
-    S.ring_head[s] = (head + n_frames) % S.ring;
-  }
-  // new pending tail = samples [n_frames*hop, total)
+  // new pending tail = samples [n_frames*hop, total) (< 512 + 160); moved through registers (overlapping ranges)
   const int keep0 = n_frames * kHop;
   const int keep = total - keep0;
-  __syncthreads();
-  // move through registers to avoid overlapping read/write hazards
-  float tmp[4];
+  float tmp[6];
   int c = 0;
-  for (int i = tid; i < keep && c < 4; i += F_THREADS, ++c) {
-    int p = keep0 + i;
+  for (int i = tid; i < keep && c < 6; i += 128, ++c) {
+    const int p = keep0 + i;
     float v;
-    if (p < np) v = pend[p];
-    else {
-      int cc = p - np;
-      float x = pcm_to_float(chunk[cc]);
-      float xp = cc > 0 ? pcm_to_float(chunk[cc - 1]) : prev;
+    if (p < np) {
+      v = pend[p];
+    } else {
+      const int cc = p - np;
+      const float x = pcm_to_float(chunk[cc]);
+      const float xp = cc > 0 ? pcm_to_float(chunk[cc - 1]) : prev;
       v = (P.a != 0.0f) ? __fsub_rn(x, __fmul_rn(P.a, xp)) : x;
     }
     tmp[c] = v;
   }
   __syncthreads();
   c = 0;
-  for (int i = tid; i < keep && c < 4; i += F_THREADS, ++c) pend[i] = tmp[c];
+  for (int i = tid; i < keep && c < 6; i += 128, ++c) pend[i] = tmp[c];
   if (tid == 0) {
     S.n_pending[s] = keep;
     if (P.n > 0) S.prev_sample[s] = pcm_to_float(chunk[P.n - 1]);
+    if (S.n_new[s] > 0) S.ring_head[s] = (S.ring_head[s] + S.n_new[s]) % S.ring;
   }
 }
-
 
 // After the encoder has produced win_post: per-stream trigger bookkeeping
 // (wakeword/tflite.py:233-239) and the reset on a VAD fall (:135-146, :241-246).
@@ -580,15 +562,20 @@ int launch_stream_filter(wwb_ctx* ctx, const int16_t* pcm, int64_t S, int64_t n,
                          const uint8_t* is_speech, const uint8_t* is_active, float a,
                          cudaStream_t st) {
   StreamFilterParams P;
-  P.pcm = pcm; P.n = n; P.is_speech = is_speech; P.is_active = is_active; P.a = a;
+  P.pcm = pcm; P.n = n; P.n_streams = S; P.is_speech = is_speech; P.is_active = is_active; P.a = a;
   P.st = ctx->st; P.L = ctx->L;
   P.hann_half = ctx->hann; P.tw256 = ctx->tw256; P.tw512 = ctx->tw512;
-  P.mp.mt = ctx->mel;
-  P.mp.mel_floor = ctx->mel_floor; P.mp.mel_log_offset = ctx->mel_log_offset; P.mp.mel_scale = ctx->mel_scale;
+  P.mp = mel_params(ctx);
   WWB_CUDA(ctx, cudaMemsetAsync(ctx->st.n_win, 0, sizeof(int32_t), st));
+  stream_plan_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(P);
+  WWB_CHECK_LAUNCH(ctx);
   size_t smem = sizeof(FilterSmem);
-  WWB_CUDA(ctx, cudaFuncSetAttribute(stream_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  stream_filter_kernel<<<(unsigned)S, F_THREADS, smem, st>>>(P);
+  WWB_CUDA(ctx, cudaFuncSetAttribute(stream_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t pairs = (S * ctx->st.max_frames + 1) / 2;
+  const int64_t grid = std::min<int64_t>((pairs + F_WARPS - 1) / F_WARPS, (int64_t)ctx->sm_count);
+  stream_frames_kernel<<<(unsigned)grid, F_THREADS, smem, st>>>(P);
+  WWB_CHECK_LAUNCH(ctx);
+  stream_tail_kernel<<<(unsigned)S, 128, 0, st>>>(P);
   WWB_CHECK_LAUNCH(ctx);
   return WWB_OK;
 }
