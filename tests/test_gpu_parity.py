@@ -342,6 +342,126 @@ def test_wavenet_config4_streaming_shape():
         assert float((posts[k - 1][:2] - ref).abs().max()) < 1e-6
 
 
+# ------------------------------------------------------------------------------------ BASELINE configs vs the oracle
+def _bench_pcm(eng, name, wake_pcm, S=512, N=160000):
+    """The headline shape: 512 streams x 10 s of device-generated PCM with the wake clip spliced into three streams
+    (start, middle, end of the batch; at the start, in the middle and at the end of the stream)."""
+    import torch
+    pcm = synth.device_pcm(S, N, seed=1234, device=eng.device)
+    wk = torch.from_numpy(wake_pcm[name]).to(eng.device)
+    for sidx, at in ((0, 0), (S // 2 - 1, 60000), (S - 1, N - wk.numel())):
+        pcm[sidx, at:at + wk.numel()] = wk
+    return pcm
+
+
+@pytest.mark.parametrize("wname,name", [("CRNN", "crnn"), ("Wavenet", "wavenet")])
+def test_bench_shape_posteriors_vs_oracle(wname, name, wake_pcm):
+    """BASELINE config 5 step shape (512 x 10 s, hop 2) through wwb_pipeline against the oracle on >= 2000 windows:
+    every window of the first / last stream, of the three streams that carry a wake clip and of two noise streams.  Decisions are exact outside the tolerance band (wakeword/tflite.py:233-239, evaluate_models.py:70-86)."""
+    w = load_weights(wname)
+    eng = get_engine(wname)
+    L = int(w["mel_length"])
+    pcm = _bench_pcm(eng, name, wake_pcm)
+    post = eng.pipeline(pcm, hop=2).cpu().numpy()
+    nw = post.shape[1]
+    assert nw == R.eval_windows(997, L)
+    checked, worst, flips = 0, 0.0, 0
+    fired = []
+    for sidx in (0, 1, 255, 300, 511):
+        mel = R.mel_stream(R.int16_to_float(pcm[sidx].cpu().numpy()), w)
+        j = np.arange(nw)
+        ref = R.posterior(mel[(2 * j)[:, None] + np.arange(L)[None, :]], w)
+        err = np.abs(post[sidx, j] - ref)
+        worst = max(worst, float(err.max()))
+        checked += j.size
+        band = np.abs(ref - 0.5) <= POST_ATOL
+        flips += int(((post[sidx, j] > 0.5) != (ref > 0.5))[~band].sum())
+        fired.append(bool((ref > 0.5).any()))
+    print("%s bench shape: %d windows checked, max |err| %.3e, %d decision flips outside the band" % (wname, checked, worst, flips))
+    assert checked >= 2000 and worst < POST_ATOL and flips == 0
+    assert fired == [True, False, True, False, True]            # the spliced clips fire, the noise streams do not
+
+
+def test_crnn_config3_vs_oracle():
+    """BASELINE config 3: 8192 independent [151, 40] windows in one wwb_posteriors call (per-window tiles, no column
+    sharing) against the oracle on 2049 of them (every 4th, and the last)."""
+    w = load_weights("CRNN")
+    eng = get_engine("CRNN")
+    pcm = synth.device_pcm(64, 160 * 300 + 512, seed=3, device=eng.device)
+    mel = eng.filter(pcm)                                    # [64, 301, 40]
+    wins = mel.unfold(1, 151, 1).permute(0, 1, 3, 2)[:, :128].reshape(-1, 151, 40).contiguous()
+    adv = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "wake_crnn_mel.npy"))
+    wins[4:4 * adv.shape[0] + 4:4] = __import__("torch").from_numpy(adv).to(eng.device)   # windows across the posterior range
+    assert wins.shape[0] == 8192
+    post = eng.posteriors(wins, hop=1)[:, 0].cpu().numpy()
+    j = np.unique(np.concatenate([np.arange(0, 8192, 4), [8191]]))
+    ref = R.posterior(wins[j].cpu().numpy(), w)
+    err = np.abs(post[j] - ref)
+    band = np.abs(ref - 0.5) <= POST_ATOL
+    print("config 3: %d windows checked, max |err| %.3e" % (j.size, err.max()))
+    assert err.max() < POST_ATOL and ref.max() > 0.9
+    assert np.array_equal((post[j] > 0.5)[~band], (ref > 0.5)[~band])
+
+
+def test_wavenet_config4_stream_push_vs_oracle(wake_pcm, w_wavenet):
+    """BASELINE config 4: 4096 streams, one new mel frame per wwb_stream_push (hop 1, 160-sample chunks), 220 pushes.
+    64 streams are checked against the oracle: 4 of them (two carry the wake clip) on every push incl. trigger latch and
+    posterior max, the others on every 8th push.  Window k = the last 182 rows of [182 zero rows ; first k+1 mel frames]
+    (wakeword/tflite.py:102, :193-215)."""
+    import torch
+    from wakeword_detection_b200 import _cabi
+    w = w_wavenet
+    S, n_push, L = 4096, 220, 182
+    eng = _cabi.Engine(w, 0, "tc")
+    eng.stream_alloc(S, 160)
+    pcm = synth.device_pcm(S, 160 * n_push, seed=21, device=eng.device)
+    wk = torch.from_numpy(wake_pcm["wavenet"]).to(eng.device)
+    full = [0, 7, 2048, 4095]
+    pcm[0, :wk.numel()] = wk[:160 * n_push]
+    pcm[2048, 1600:1600 + wk.numel()] = wk[:160 * n_push - 1600]
+    part = [int(s) for s in np.linspace(1, 4094, 60).astype(int)]
+    posts, trigs, pmax = [], [], None
+    active = torch.zeros(S, dtype=torch.uint8, device=eng.device)
+    for i in range(n_push):
+        post, npost, trig, pmax = eng.stream_push(pcm[:, i * 160:(i + 1) * 160].contiguous(), is_active=active)
+        want = 0 if (i + 1) * 160 < 512 else 1
+        act = active.bool()
+        assert bool((npost[~act] == want).all()) and bool((npost[act] == 0).all())
+        active |= trig
+        posts.append(post[:, 0].clone())
+        trigs.append(trig.clone())
+    posts = torch.stack(posts).cpu().numpy()            # [push, stream]
+    trigs = torch.stack(trigs).cpu().numpy().astype(bool)
+    first_frame_push = 3                                # 512 samples are complete during push 3 (0-based)
+    checked, worst = 0, 0.0
+    for sidx in full + part:
+        mel = R.mel_stream(R.int16_to_float(pcm[sidx].cpu().numpy()), w)
+        padded = np.concatenate([np.zeros((L, 40), np.float32), mel])
+        ks = np.arange(mel.shape[0]) if sidx in full else np.arange(0, mel.shape[0], 8)
+        ref = R.posterior(padded[(ks + 1)[:, None] + np.arange(L)[None, :]], w)
+        got = posts[ks + first_frame_push, sidx]
+        live = ~np.isnan(got)                           # after the trigger latched the stream stops sampling (:139-140)
+        err = np.abs(got[live] - ref[live])
+        worst = max(worst, float(err.max()))
+        checked += int(live.sum())
+        if sidx in full:
+            over = np.nonzero(ref > 0.5)[0]
+            band = np.abs(ref - 0.5) <= POST_ATOL
+            if over.size and not band.any():
+                k0 = int(over[0])
+                assert trigs[k0 + first_frame_push, sidx] and trigs[:, sidx].sum() == 1
+                assert np.isnan(posts[k0 + first_frame_push + 1:, sidx]).all()
+                assert abs(float(pmax[sidx]) - ref[:k0 + 1].max()) < POST_ATOL
+            elif not over.size:
+                assert not trigs[:, sidx].any() and live.all()
+                assert abs(float(pmax[sidx]) - ref.max()) < POST_ATOL
+    print("config 4: %d pushes checked on 64 streams, max |err| %.3e" % (checked, worst))
+    assert worst < POST_ATOL and checked >= 2000
+    assert trigs[:, 0].any() and trigs[:, 2048].any()
+    eng.close()
+
+
+
 # ------------------------------------------------------------------------------------ counters
 def test_eval_counts_vs_oracle(golden):
     eng = get_engine("CRNN")
