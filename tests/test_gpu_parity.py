@@ -684,6 +684,28 @@ def test_crnn_shared_columns_bit_identical_to_per_window_path(S, F, hop):
     assert float((b - f32.posteriors(X, hop=hop)).abs().max()) < 1e-4
 
 
+@pytest.mark.parametrize("S,F,hop", [(2, 411, 2), (5, 998, 2), (2, 700, 1), (3, 640, 4), (2, 1200, 8), (1, 196, 2), (40, 998, 2),
+                                     (3, 641, 2), (2, 1100, 2), (2, 1101, 1), (1, 1561, 3)])   # 640 / 1100 / 1560: chunk boundaries of the stream pass
+def test_wavenet_shared_activations_bit_identical_to_per_window_path(S, F, hop):
+    """Sliding-window batches take every activation outside the causal-padding cone from a stream-level pass
+    (wavenet_tc.cu, header); WWB_WN_NO_SHARE=1 computes every window on its own.  Same MMAs on the same operand values:
+    identical bits; and both agree with the fp32 CUDA-core path."""
+    import os
+    import torch
+    tc, f32 = get_engine("Wavenet", "tc"), get_engine("Wavenet", "f32")
+    torch.manual_seed(S * 1000 + F)
+    X = torch.rand((S, F, 40), device=tc.device) * 5
+    os.environ["WWB_WN_NO_SHARE"] = "1"
+    try:
+        a = tc.posteriors(X, hop=hop).clone()
+    finally:
+        os.environ["WWB_WN_NO_SHARE"] = "0"
+    b = tc.posteriors(X, hop=hop).clone()
+    assert float((a - f32.posteriors(X, hop=hop)).abs().max()) < 1e-4
+    assert float((a - b).abs().max()) < 1e-5
+    assert bool((a == b).all())
+
+
 @pytest.mark.parametrize("wname,name", [("CRNN", "crnn"), ("Wavenet", "wavenet")])
 def test_tf_lite_opts_models_predict_dropin(wname, name):
     """utils/evaluate_tf_lite_opts.py:49-67: clips -> posterior -> non-strict `>= threshold`, here as one batch."""

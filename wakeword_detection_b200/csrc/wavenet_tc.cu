@@ -1,10 +1,21 @@
 // K5/K6 — WaveNet encode + detect on the tensor cores (precision WWB_PREC_TC / TC_FAST).
 //
-// One persistent CTA per SM processes groups of WN_G = 3 windows.  The rows of a group
-// (window w, time t) -> o = w*198 + t form the M dimension of every GEMM (5 tiles of 128
-// rows; the 16 rows after each window are the next window's causal zero padding).  Each of
-// the 640 epilogue threads owns ONE row for the whole 24-block stack: its 16-channel
-// residual stream and 32-channel skip sum never leave registers.  Per block and tile:
+// One persistent CTA per SM processes groups of WN_G = 3 windows.  The rows of a group are interleaved
+// TIME-MAJOR: (time t, window w) -> o = t*3 + w form the M dimension of every GEMM (5 tiles of 128 rows, 546 of the
+// 640 rows are real; the 48 rows in front of row 0 are the causal zero padding of all three windows).  A dilated tap
+// is still a linear row shift (3*d rows).  Each of the 640 epilogue threads owns ONE row for the whole 24-block
+// stack: its 16-channel residual stream and 32-channel skip sum never leave registers.
+//
+// SHARED ACTIVATIONS (sliding-window batches).  Row t of block b depends on the window's zero padding only while
+// t < D(b) = sum_{m<=b} 2*dilation[m] (2, 6, 14, 30, 32, ... 180): every other activation is a function of the
+// stream's absolute frame and identical in all ~91 windows that cover it.  With time-major rows the window-dependent
+// ("dirty") rows of a block are a PREFIX, so tile i only has to take part from block join[i] = min{b : D(b) > t_min(i)}
+// on (0, 6, 11, 18, 23 for the shipped model: 62 instead of 120 tile-blocks per group).  A tile joins from per-frame
+// SNAPSHOTS (residual stream x and the skip prefix sum after block join[i]-1; 192 B per frame and level) written by a
+// stream-level pass of this same kernel (stream_mode: a group is a chunk of 640 consecutive frames of one stream,
+// rows o >= 180 of a chunk are past every receptive field; +1.5 % work).  Same MMAs on the same operand values in the
+// same order, so the posteriors are bit-identical to the per-window formulation (WWB_WN_NO_SHARE=1 forces it).
+// Per block and tile:
 //   gate GEMM   D[128,32] = sum_tap U[rows - (2-tap)*d, 16] * Wg_tap          (tcgen05, TMEM)
 //               taps 0/1 (row-shifted) read A from shared memory: the operand layout is linear
 //               in the row index, so a dilated tap is a start-address offset;
@@ -25,8 +36,8 @@
 // The per-block BatchNorm affine u = bn_mul * x + bn_add is FOLDED into the gate GEMM (weights * bn_mul, bias +
 // W * bn_add), so the A operand is the residual stream x itself and the epilogue neither loads the 32 constants
 // (8 broadcast LDS.128 = 32 shared-memory wavefronts per warp and block, 17 % of the shared-memory pipe) nor
-// applies them.  The causal zero padding is of u, not x: the 16 padding rows in front of every window therefore
-// hold x_pad = -bn_add / bn_mul (so that u_pad = 0), rewritten for each block by the threads that own those rows.
+// applies them.  The causal zero padding is of u, not x: the 48 padding rows in front of row 0 therefore
+// hold x_pad = -bn_add / bn_mul (so that u_pad = 0), rewritten for each block by the threads of rows 0..47.
 // fp16 hi/lo operand split (3 MMAs per product) keeps the result at fp32 accuracy
 // (DESIGN.md §precision).  Epilogue arithmetic uses the packed fp32x2 instructions (FFMA2/FADD2).
 // Per-block weights (12 KB incl. the bias operands) stream through a 4-stage cp.async.bulk ring.
@@ -36,7 +47,7 @@
 // same time); a second extra warp issues the small res/skip GEMMs, so they never queue behind a wait of the
 // gate warp.  Epilogue 2 is split: 2a (residual -> u) releases the next gate GEMM, 2b (skip sum) overlaps it.
 // Ordering rules:
-//   gate(k,i) needs epilogue 2 of (k-1,i) and (k-1,i-1)      (its taps reach 16 rows into tile i-1)
+//   gate(k,i) needs epilogue 2 of (k-1,i) and (k-1,i-1)      (its taps reach up to 48 rows into tile i-1)
 //   rs(k,i)   needs epilogue 1 of (k,i) and gate(k,i+1) COMPLETE: epilogue 2 of (k,i) overwrites rows that
 //             GEMM reads, and GEMMs issued by different threads have no implicit order.
 #include <string.h>
@@ -49,10 +60,14 @@ namespace wwb {
 using namespace tc;
 
 constexpr int WN_G = 3;                       // windows per group
-constexpr int WN_SLOT = 198;                  // rows per window slot (182 + 16 pad)
 constexpr int WN_NT = 5;                      // M tiles per group
 constexpr int WN_ROWS = WN_NT * 128;          // 640
-constexpr int WN_UROWS = WN_ROWS + 16;        // U buffer has 16 leading zero rows
+constexpr int WN_PAD = 48;                    // leading padding rows of the U buffer: 2 * max dilation (8) * WN_G
+constexpr int WN_UROWS = WN_ROWS + WN_PAD;
+constexpr int WN_MAXT = 182;                  // WN_G * 182 = 546 rows <= WN_ROWS
+constexpr int WN_CHUNK_WARM = 180;            // stream mode: rows of a chunk inside some receptive field (D(23) = 180)
+constexpr int WN_CHUNK_STEP = WN_ROWS - WN_CHUNK_WARM;
+constexpr int WN_SNAP_F = 48;                 // floats per snapshot row: x[16], skip prefix sum[32]
 constexpr int WN_PU = WN_UROWS * 16;          // bytes per U chunk panel
 constexpr int WN_EPI_WARPS = WN_NT * 4;       // 20
 constexpr int WN_EPI_THREADS = WN_EPI_WARPS * 32;
@@ -85,11 +100,13 @@ struct WnSmem {
   unsigned char W[WN_WST][WN_WBLK];
   WnHead head;
   uint64_t bar_gate[WN_NT], bar_rs[WN_NT], bar_det[WN_NT];   // GEMM completion (tcgen05.commit) -> the tile's four warps
-  uint64_t bar_u[WN_NT];                     // the tile's four warps finished epilogue 2 -> gate warp
+  uint64_t bar_u[WN_NT];                     // the tile's four warps finished epilogue 2 (tile 0: + the padding rows, written by the res/skip warp) -> gate warp
+  uint64_t bar_dq[WN_NT];                    // the tile's four warps stored the detect head's input -> gate warp
   uint64_t bar_g[WN_NT];                     // the tile's four warps finished epilogue 1 -> res/skip warp
   uint64_t wfull[WN_WST];
   uint32_t tmem_base;
   int zmax[2][WN_G][2];                      // per-window max of the two logits, double-buffered by group parity
+  int zcnt[2];                               // warps that have added their rows to zmax[parity]: the last one finalises the group
 };
 
 struct WnTcParams {
@@ -100,12 +117,26 @@ struct WnTcParams {
   int L;
   int nsplit;
   int dil[24];                  // dilation per block (kernel-parameter space keeps it in uniform registers)
+  int rstride;                  // rows per time step: WN_G (window groups, row = t*3 + w) or 1 (stream chunks)
+  int stream_mode;              // 1: a group is a chunk of WN_ROWS consecutive frames of one stream; writes snapshots
+  int chunks_per_stream;
+  int join[WN_NT];              // first block tile i takes part in (0 = from the input layer)
+  int src_slot[WN_NT];          // snapshot slot a joining tile starts from (-1: input layer x0, skip = 0)
+  int snap_slot[24];            // stream mode: snapshot slot written after block k (-1: none)
+  float* snap;                  // [n_slots][n_rows][WN_SNAP_F]
+  int64_t n_rows;               // rows behind x0 / snap (n_streams * ring)
   float* enc_out;
   float* det_out;
   float* post;
   long long* dbg;   // optional timeline dump (block 0, second group): [8 roles][2 groups x 24 blocks][4 events]
 };
 
+// fine-grained chain stamps of tile 0 (first timed group): [24 blocks][16 events] behind the hang-report area
+#ifdef WWB_WN_DBG2
+#define WN_DBG2(k, ev) do { if (P.dbg && blockIdx.x == 0 && grp == (int64_t)gridDim.x) P.dbg[8 * 48 * 4 + 64 + (k) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define WN_DBG2(k, ev) do { } while (0)
+#endif
 #define WN_DBG(role, k, ev) do { if (P.dbg && blockIdx.x == 0 && (grp == (int64_t)gridDim.x || grp == 2 * (int64_t)gridDim.x)) P.dbg[((role) * 48 + (k) + (grp == (int64_t)gridDim.x ? 0 : 24)) * 4 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -173,7 +204,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
   const int64_t n_win = P.wm.n_win_dev ? (int64_t)*P.wm.n_win_dev : P.wm.n_win;
-  const int64_t n_groups = (n_win + WN_G - 1) / WN_G;
+  const int64_t n_groups = P.stream_mode ? P.wm.n_streams * (int64_t)P.chunks_per_stream : (n_win + WN_G - 1) / WN_G;
   const int L = P.L;
 
   // ---- one-time setup ----
@@ -181,10 +212,11 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
   for (int i = tid; i < (int)(sizeof(WnHead) / 16); i += WN_THREADS)
     reinterpret_cast<uint4*>(&sm.head)[i] = reinterpret_cast<const uint4*>(P.head)[i];
   if (tid < 2 * WN_G * 2) (&sm.zmax[0][0][0])[tid] = WN_KEY_NEG_INF;
+  if (tid < 2) sm.zcnt[tid] = 0;
   if (tid == 0) {
     for (int i = 0; i < WN_NT; ++i) {
-      mbar_init(&sm.bar_u[i], 4); mbar_init(&sm.bar_g[i], 4); mbar_init(&sm.bar_gate[i], 1); mbar_init(&sm.bar_rs[i], 1);
-      mbar_init(&sm.bar_det[i], 1);
+      mbar_init(&sm.bar_u[i], i == 0 ? 5 : 4); mbar_init(&sm.bar_g[i], 4); mbar_init(&sm.bar_gate[i], 1); mbar_init(&sm.bar_rs[i], 1);
+      mbar_init(&sm.bar_det[i], 1); mbar_init(&sm.bar_dq[i], 4);
     }
     for (int s = 0; s < WN_WST; ++s) mbar_init(&sm.wfull[s], 1);
     mbar_fence_init();
@@ -202,23 +234,12 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     // =========================== epilogue threads: one row each ===========================
     const int tile = warp >> 2, q = warp & 3;
     const int o = tile * 128 + q * 32 + lane;       // row within the group
-    const int w = o / WN_SLOT, t = o - w * WN_SLOT;
+    const int R = P.rstride;
+    const int t = o / R, w = o - t * R;             // time step, window (stream mode: R = 1, t = frame offset in the chunk)
     const uint32_t tacc = tmem + tile * WN_TMEM_TILE;                 // this tile's TMEM columns (lane 0)
     const uint32_t tbase = tacc + ((uint32_t)(q * 32) << 16);         // ... seen from this warp's lane quadrant
-    uint32_t n_gate = 0, n_rs = 0, n_w = 0, n_u = 0;  // completed phases of bar_gate / bar_rs ; global block index ; groups done
-    unsigned char* const Urow = sm.U + (16 + o) * 16;
-    // padding rows: the 16 rows after each window (they precede the next one; owned by otherwise idle threads) and,
-    // for window 0, U rows 0..15, which the threads of rows 0..15 write in addition to their own row (they belong to
-    // tile 0, whose gate GEMM is the reader, so the tile's arrival barrier orders the write)
-    const bool pad_row = (w < WN_G && t >= 182) || (o < 16);
-    unsigned char* const Upad = (o < 16) ? sm.U + o * 16 : Urow;
-    auto store_pad = [&](const unsigned char* chunk) {   // chunk: 64 bytes (hi0, hi1, lo0, lo1)
-      const uint4* c4 = reinterpret_cast<const uint4*>(chunk);
-      *reinterpret_cast<uint4*>(Upad) = c4[0];
-      *reinterpret_cast<uint4*>(Upad + WN_PU) = c4[1];
-      *reinterpret_cast<uint4*>(Upad + 2 * WN_PU) = c4[2];
-      *reinterpret_cast<uint4*>(Upad + 3 * WN_PU) = c4[3];
-    };
+    uint32_t n_gate = 0, n_rs = 0, n_u = 0;  // completed phases of bar_gate / bar_rs ; groups done
+    unsigned char* const Urow = sm.U + (WN_PAD + o) * 16;
     {
       uint32_t one[16];
 #pragma unroll
@@ -228,69 +249,86 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       tmem_st_wait();
     }
     const u64 ZERO2 = pk(0.f, 0.f), ONE2 = pk(1.f, 1.f);
+    const int jn = P.join[tile];            // first block of this tile
+    const int src_slot = P.src_slot[tile];  // where its rows start from
+    const bool stream_mode = P.stream_mode != 0;
 
-    // The input layer x0 = ReLU(in_w * mel + in_b) depends only on the mel row, and every mel row is shared by ~91
-    // overlapping windows: it is computed once per row by wn_input_kernel (64 B per row instead of 160 B of mel per row
-    // and window), which also takes a tcgen05.st / GEMM / tcgen05.ld round trip off the group-boundary chain.  The row
-    // of the NEXT group is fetched into registers before this group's detect epilogue (x / skip are dead by then), so
-    // its global-memory latency is not on that chain either.
-    float4 xrow[4];
-    auto fetch_x0 = [&](int64_t grp_next) {
-      const int64_t bn = grp_next * WN_G + w;
-      const bool vn = (grp_next < n_groups) && (w < WN_G) && (t < L) && (bn < n_win);
-      int64_t s0 = 0;
-      int start = 0;
-      if (vn) win_origin(P.wm, bn, s0, start);
-      int rr = start + (vn ? t : 0);
-      if (rr >= P.wm.ring) rr -= P.wm.ring;
-      const float4* row = reinterpret_cast<const float4*>(P.x0 + (s0 * P.wm.ring + rr) * 16);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) xrow[i] = vn ? __ldg(row + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    int64_t fin_grp = -1;
-    int fin_zp = 0;
-    auto finalise = [&]() {
-      if (fin_grp >= 0 && tid < WN_G) {
-        const int64_t bb = fin_grp * WN_G + tid;
-        if (bb < n_win) {
-          const float a0 = key2f(sm.zmax[fin_zp][tid][0]), a1 = key2f(sm.zmax[fin_zp][tid][1]);
-          const float m = fmaxf(a0, a1);
-          const float e0 = expf(a0 - m), e1 = expf(a1 - m), s = e0 + e1;
-          if (P.det_out) { P.det_out[bb * 2] = e0 / s; P.det_out[bb * 2 + 1] = e1 / s; }
-          if (P.post) P.post[bb] = e1 / s;
-        }
-        sm.zmax[fin_zp][tid][0] = WN_KEY_NEG_INF;   // for the group after next
-        sm.zmax[fin_zp][tid][1] = WN_KEY_NEG_INF;
+    // Start state of a row: the input layer x0 = ReLU(in_w * mel + in_b) (computed once per mel row by wn_input_kernel)
+    // with an empty skip sum, or - for a tile that joins at block jn > 0 - the stream-level snapshot after block jn-1.
+    // The state of the NEXT group is fetched straight into x / skip before this group's detect epilogue (both are dead
+    // by then), so its global-memory latency is not on the group-boundary chain.
+    u64 x[8], skip[16];     // channel pairs
+    bool valid = false, snap_out = false;
+    int64_t b = 0;
+    float* snap_dst = nullptr;
+    auto fetch_state = [&](int64_t g) {
+      bool vn = g < n_groups;
+      int64_t row = 0;
+      snap_out = false;
+      if (stream_mode) {
+        const int64_t s0 = g / P.chunks_per_stream;
+        const int c = (int)(g - s0 * P.chunks_per_stream);
+        const int f = c * WN_CHUNK_STEP + o;
+        vn = vn && f < P.wm.ring;
+        row = s0 * P.wm.ring + (vn ? f : 0);
+        snap_out = vn && (c == 0 || o >= WN_CHUNK_WARM);
+        snap_dst = P.snap + row * WN_SNAP_F;
+      } else {
+        b = g * WN_G + w;
+        vn = vn && (t < L) && (b < n_win);
+        int64_t s0 = 0;
+        int start = 0;
+        if (vn) win_origin(P.wm, b, s0, start);
+        int rr = start + (vn ? t : 0);
+        if (rr >= P.wm.ring) rr -= P.wm.ring;
+        row = s0 * P.wm.ring + rr;
       }
-      fin_grp = -1;
-    };
-    if ((int64_t)blockIdx.x < n_groups) fetch_x0(blockIdx.x);
-    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++n_u) {
-      const int64_t b = grp * WN_G + w;
-      const bool valid = (w < WN_G) && (t < L) && (b < n_win);
-      u64 x[8], skip[16];     // channel pairs
-      // ---- input layer: x = x0 row (prefetched); block 0's BatchNorm is folded into its gate weights ----
-      {
-        if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 0);
-        finalise();   // previous group's posteriors
-#pragma unroll
-        for (int n = 0; n < 16; ++n) skip[n] = ZERO2;
-        uint32_t ur[16];
+      valid = vn;
+      if (src_slot >= 0) {
+        const float4* p = reinterpret_cast<const float4*>(P.snap + ((int64_t)src_slot * P.n_rows + row) * WN_SNAP_F);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          x[2 * i] = pk(xrow[i].x, xrow[i].y);
-          x[2 * i + 1] = pk(xrow[i].z, xrow[i].w);
-          split2(x[2 * i], ur[2 * i], ur[8 + 2 * i]);
-          split2(x[2 * i + 1], ur[2 * i + 1], ur[8 + 2 * i + 1]);
+          const float4 v = vn ? __ldg(p + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[2 * i] = pk(v.x, v.y);
+          x[2 * i + 1] = pk(v.z, v.w);
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = vn ? __ldg(p + 4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          skip[2 * i] = pk(v.x, v.y);
+          skip[2 * i + 1] = pk(v.z, v.w);
+        }
+      } else {
+        const float4* p = reinterpret_cast<const float4*>(P.x0 + row * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = vn ? __ldg(p + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[2 * i] = pk(v.x, v.y);
+          x[2 * i + 1] = pk(v.z, v.w);
+        }
+#pragma unroll
+        for (int n = 0; n < 16; ++n) skip[n] = ZERO2;
+      }
+    };
+    fetch_state(blockIdx.x);
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++n_u) {
+      const bool valid_g = valid;             // (fetch_state of the next group overwrites `valid` before the detect epilogue)
+      const bool snap_g = snap_out;
+      float* const snap_g_dst = snap_dst;
+      const int64_t b_g = b;
+      // ---- start state -> U row (operand of the first gate GEMM); that block's BatchNorm is folded into its gate weights ----
+      {
+        if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 0);
+        uint32_t ur[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split2(x[i], ur[i], ur[8 + i]);
         if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 1);
-        if (valid) {
+        if (valid_g) {
           *reinterpret_cast<uint4*>(Urow) = make_uint4(ur[0], ur[1], ur[2], ur[3]);
           *reinterpret_cast<uint4*>(Urow + WN_PU) = make_uint4(ur[4], ur[5], ur[6], ur[7]);
           *reinterpret_cast<uint4*>(Urow + 2 * WN_PU) = make_uint4(ur[8], ur[9], ur[10], ur[11]);
           *reinterpret_cast<uint4*>(Urow + 3 * WN_PU) = make_uint4(ur[12], ur[13], ur[14], ur[15]);
         }
-        if (pad_row) store_pad(sm.head.pad0);
         tmem_st16(tbase + WN_C_U, ur);
         tmem_st_wait();
         fence_before_sync();
@@ -299,15 +337,13 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         if (lane == 0) mbar_arrive(&sm.bar_u[tile]);
       }
 
-      for (int k = 0; k < 24; ++k, ++n_w) {
-        const int ws = n_w % WN_WST;
-        const float* wf = reinterpret_cast<const float*>(sm.W[ws] + WN_OFF_F32);
-        WN_MBAR_WAIT(&sm.wfull[ws], (n_w / WN_WST) & 1, 4);   // BN constants travel with the block's weights (off the critical path: the gate GEMM is running)
+      for (int k = jn; k < 24; ++k) {
         // ---- epilogue 1: gated activation ----
         WN_MBAR_WAIT(&sm.bar_gate[tile], n_gate & 1, 5);
         ++n_gate;
         fence_after_sync();
         if (q == 0 && lane == 0) WN_DBG(tile, k, 0);
+        if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 0);
         {
           uint32_t gr[16];
 #pragma unroll
@@ -316,6 +352,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             tmem_ld8(tbase + h8 * 8, at);
             tmem_ld8(tbase + 16 + h8 * 8, as);
             tmem_ld_wait();
+            if (h8 == 0 && tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 1);
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
               // accumulators arrive as a2 = -2*log2(e)*(a + b_t), b2 = -log2(e)*(b + b_s) (scaled weights, bias GEMM)
@@ -334,19 +371,23 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
               split2(g, gr[h8 * 4 + p], gr[8 + h8 * 4 + p]);
             }
           }
+          if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 2);
           tmem_st16(tbase + WN_C_G, gr);
           tmem_st_wait();
+          if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 3);
         }
         fence_before_sync();
         if (q == 0 && lane == 0) WN_DBG(tile, k, 1);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.bar_g[tile]);
+        if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 4);
 
         // ---- epilogue 2a: residual, next block's BN -> u (releases the next gate GEMM) ----
         WN_MBAR_WAIT(&sm.bar_rs[tile], n_rs & 1, 6);
         ++n_rs;
         fence_after_sync();
         if (q == 0 && lane == 0) WN_DBG(tile, k, 2);
+        if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 5);
         const bool last = (k == 23);
         if (!last) {
           uint32_t ur[16];
@@ -362,20 +403,22 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
               split2(x[c], ur[c], ur[8 + c]);   // the next block's BN is folded into its gate weights
             }
           }
-          if (valid) {
+          if (valid_g) {
             *reinterpret_cast<uint4*>(Urow) = make_uint4(ur[0], ur[1], ur[2], ur[3]);
             *reinterpret_cast<uint4*>(Urow + WN_PU) = make_uint4(ur[4], ur[5], ur[6], ur[7]);
             *reinterpret_cast<uint4*>(Urow + 2 * WN_PU) = make_uint4(ur[8], ur[9], ur[10], ur[11]);
             *reinterpret_cast<uint4*>(Urow + 3 * WN_PU) = make_uint4(ur[12], ur[13], ur[14], ur[15]);
           }
-          if (pad_row) store_pad(reinterpret_cast<const unsigned char*>(wf) + 320);
+          if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 6);
           tmem_st16(tbase + WN_C_U, ur);
           tmem_st_wait();
+          if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 8);
           fence_before_sync();
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.bar_u[tile]);
           if (q == 0 && lane == 0) WN_DBG(tile, k, 3);
+          if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 9);
         }
         // ---- epilogue 2b: skip sum (off the critical path: the next gate GEMM is already running) ----
 #pragma unroll
@@ -387,6 +430,27 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           for (int p = 0; p < 4; ++p) skip[h8 * 4 + p] = add_relu2(skip[h8 * 4 + p], pk(s[2 * p], s[2 * p + 1]));
         }
         fence_before_sync();
+        if (stream_mode) {
+          // stream-level pass: x and the skip prefix sum after this block, for the window tiles that join at block k+1
+          const int sl = P.snap_slot[k];
+          if (sl >= 0 && snap_g) {
+            float4* dst = reinterpret_cast<float4*>(snap_g_dst + (int64_t)sl * P.n_rows * WN_SNAP_F);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float a0, a1, a2, a3;
+              upk(x[2 * i], a0, a1);
+              upk(x[2 * i + 1], a2, a3);
+              dst[i] = make_float4(a0, a1, a2, a3);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float a0, a1, a2, a3;
+              upk(skip[2 * i], a0, a1);
+              upk(skip[2 * i + 1], a2, a3);
+              dst[4 + i] = make_float4(a0, a1, a2, a3);
+            }
+          }
+        }
         if (last) {
           // detect input: ReLU(skip) hi/lo; channels 0-15 -> the u columns, 16-31 -> the g columns
           uint32_t er[16];
@@ -399,13 +463,13 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           tmem_st_wait();
           fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.bar_u[tile]);
+          if (lane == 0) mbar_arrive(&sm.bar_dq[tile]);
           if (q == 0 && lane == 0) WN_DBG(tile, k, 3);
         }
       }
 
-      if (P.enc_out && valid) {
-        float4* dst = reinterpret_cast<float4*>(P.enc_out + (b * L + t) * 32);
+      if (P.enc_out && valid_g) {
+        float4* dst = reinterpret_cast<float4*>(P.enc_out + (b_g * L + t) * 32);
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
           float s0, s1, s2, s3;
@@ -415,7 +479,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         }
       }
       if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 0);   // boundary timeline: e2b(23) done
-      fetch_x0(grp + gridDim.x);   // next group's input row: in flight during the detect epilogue
+      fetch_state(grp + gridDim.x);   // next group's start state: in flight during the detect epilogue
       // ---- detect head epilogue: ReLU(D + b1) -> 32->2 -> max over time ----
       WN_MBAR_WAIT(&sm.bar_det[tile], n_u & 1, 8);
       fence_after_sync();
@@ -441,39 +505,57 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           acc1[0] = ffma2(w1a.x, e0, acc1[0]); acc1[1] = ffma2(w1a.y, e1, acc1[1]);
           acc1[0] = ffma2(w1b.x, e2, acc1[0]); acc1[1] = ffma2(w1b.y, e3, acc1[1]);
         }
-        float a, b;
-        upk(fadd2(acc0[0], acc0[1]), a, b);
-        z0 = (a + b) + sm.head.det2_b[0];
-        upk(fadd2(acc1[0], acc1[1]), a, b);
-        z1 = (a + b) + sm.head.det2_b[1];
+        float fa, fb;
+        upk(fadd2(acc0[0], acc0[1]), fa, fb);
+        z0 = (fa + fb) + sm.head.det2_b[0];
+        upk(fadd2(acc1[0], acc1[1]), fa, fb);
+        z1 = (fa + fb) + sm.head.det2_b[1];
       }
       fence_before_sync();
       const int zp = (int)(n_u & 1);
-      {
-        // a warp's 32 rows touch at most two windows (slot = 198 rows): one reduction + one atomic per window
-        const int w_first = __shfl_sync(0xffffffffu, w, 0);
+      if (!stream_mode) {
+        // a warp's 32 rows are ~11 time steps of all three windows: one reduction + one atomic per window and logit
 #pragma unroll
-        for (int dw = 0; dw < 2; ++dw) {
-          const bool mine = valid && (w == w_first + dw);
+        for (int dw = 0; dw < WN_G; ++dw) {
+          const bool mine = valid_g && (w == dw);
           const unsigned m = __ballot_sync(0xffffffffu, mine);
           if (m) {
             const int k0 = __reduce_max_sync(0xffffffffu, mine ? f2key(z0) : WN_KEY_NEG_INF);
             const int k1 = __reduce_max_sync(0xffffffffu, mine ? f2key(z1) : WN_KEY_NEG_INF);
             if (lane == 0) {
-              atomicMax(&sm.zmax[zp][w_first + dw][0], k0);
-              atomicMax(&sm.zmax[zp][w_first + dw][1], k1);
+              atomicMax(&sm.zmax[zp][dw][0], k0);
+              atomicMax(&sm.zmax[zp][dw][1], k1);
             }
           }
         }
+        if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 2);   // detect epilogue done
+        // No CTA barrier at the group boundary: the LAST of the 20 warps to add its rows turns the maxima into posteriors
+        // and clears them.  zmax / zcnt are double-buffered by group parity; the tiles of a CTA are never more than a few
+        // blocks apart (each gate GEMM needs the tile below one block back), so group g + 2 cannot reach this point before
+        // group g has been finalised.
+        if (lane == 0) {
+          __threadfence_block();
+          if (atomicAdd(&sm.zcnt[zp], 1) == WN_EPI_WARPS - 1) {
+            __threadfence_block();
+            for (int dw = 0; dw < WN_G; ++dw) {
+              const int64_t bb = grp * WN_G + dw;
+              const float a0 = key2f(sm.zmax[zp][dw][0]), a1 = key2f(sm.zmax[zp][dw][1]);
+              sm.zmax[zp][dw][0] = WN_KEY_NEG_INF;
+              sm.zmax[zp][dw][1] = WN_KEY_NEG_INF;
+              if (bb < n_win) {
+                const float m = fmaxf(a0, a1);
+                const float e0 = expf(a0 - m), e1 = expf(a1 - m), sden = e0 + e1;
+                if (P.det_out) { P.det_out[bb * 2] = e0 / sden; P.det_out[bb * 2 + 1] = e1 / sden; }
+                if (P.post) P.post[bb] = e1 / sden;
+              }
+            }
+            sm.zcnt[zp] = 0;
+          }
+        }
+        __syncwarp();
       }
-      if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 2);   // detect epilogue done
-      epi_bar_sync();   // the only barrier per group: zmax is double-buffered, and its reset (in finalise, which runs
-                        // before the barrier of group g+1) is ordered before the atomics of group g+2
-      fin_grp = grp;    // softmax + stores of this group's posteriors: deferred into the next group's input-GEMM wait
-      fin_zp = zp;
-      if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 3);   // barrier done
+      if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 3);
     }
-    finalise();
   } else if (warp == WN_EPI_WARPS) {
     // =========================== gate-GEMM warp + weight loader ===========================
     // Issues the gate GEMMs tile after tile, each as soon as the tile's epilogue 2 has arrived.  Because one
@@ -495,22 +577,29 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         bulk_g2s(sm.W[n], P.wblob + (size_t)n * WN_WBLK, WN_WBLK, &sm.wfull[n]);
       }
     uint32_t n_w = 0;         // global block index (24 per group)
-    uint32_t ubase = 0;       // bar_u phases before this group (25 per group)
-    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ubase += 25, ++n_u) {
+    uint32_t cu[WN_NT];       // consumed phases of bar_u, per tile (a tile that joins at block j has 24 - j per group)
+#pragma unroll
+    for (int i = 0; i < WN_NT; ++i) cu[i] = 0;
+    const uint32_t rs3 = (uint32_t)P.rstride;
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++n_u) {
       for (int k = 0; k < 24; ++k, ++n_w) {
         WN_MBAR_WAIT(&sm.wfull[n_w % WN_WST], (n_w / WN_WST) & 1, 1);
-        const uint32_t d = (uint32_t)P.dil[k];
+        const uint32_t d = (uint32_t)P.dil[k] * rs3;     // tap distance in rows
         const uint64_t wofs = (uint64_t)((n_w % WN_WST) * (WN_WBLK >> 4));
         const uint64_t b0 = dWg + wofs, bb = dBg + wofs;
 #pragma unroll
         for (int i = 0; i < WN_NT; ++i) {
+          if (k < P.join[i]) continue;                   // the tile's rows are still shared (stream-level) activations
           if (i == 1) WN_DBG(6, k, 0);
-          WN_MBAR_WAIT(&sm.bar_u[i], (ubase + k) & 1, 2);
+          if (i == 0 && lane == 0) WN_DBG2(k, 10);
+          WN_MBAR_WAIT(&sm.bar_u[i], cu[i] & 1, 2);
+          ++cu[i];
+          if (i == 0 && lane == 0) WN_DBG2(k, 11);
           if (i == 1) WN_DBG(6, k, 1);
           fence_after_sync();
           if (elect_one()) {   // one lane issues the whole tile (uniform descriptors, no per-MMA election)
             const uint32_t tacc = tmem + i * WN_TMEM_TILE;
-            const uint64_t a0 = dU + (uint64_t)(16 + i * 128 - 2 * d), a1 = dU + (uint64_t)(16 + i * 128 - d);
+            const uint64_t a0 = dU + (uint64_t)(WN_PAD + i * 128 - 2 * d), a1 = dU + (uint64_t)(WN_PAD + i * 128 - d);
             const uint64_t lo_a = (uint64_t)((2 * WN_PU) >> 4), lo_b = (uint64_t)(3072 >> 4);
             mma_f16_ss(tacc, a0, b0, idesc_gate, false);
             if (nsplit == 3) {
@@ -529,13 +618,14 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             }
             mma_f16_ts(tacc, tmem + WN_C_ONE, bb, idesc_gate, true);
             mma_commit(&sm.bar_gate[i]);
+            if (i == 0) WN_DBG2(k, 12);
             if (i == 0) WN_DBG(5, k, 0);
             if (i == WN_NT - 1) WN_DBG(5, k, 1);
           }
           __syncwarp();
           if (i == 1) WN_DBG(6, k, 2);
         }
-        // every tile has finished block n_w-1 (its epilogue 2 was awaited above): refill that stage
+        // every active tile has finished block n_w-1 (its epilogue 2 was awaited above): refill that stage
         if (n_w >= 1 && n_w - 1 + WN_WST < total_loads) {
           const uint32_t nl = n_w - 1 + WN_WST;
           if (lane == 0) {
@@ -547,7 +637,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       // detect head: D[128,32] = ReLU(skip)[128,32] * W1^T ; k-step 0 from the u columns, k-step 1 from the g columns
 #pragma unroll
       for (int i = 0; i < WN_NT; ++i) {
-        WN_MBAR_WAIT(&sm.bar_u[i], (ubase + 24) & 1, 9);
+        WN_MBAR_WAIT(&sm.bar_dq[i], n_u & 1, 9);
         fence_after_sync();
         if (elect_one()) {
           const uint32_t tacc = tmem + i * WN_TMEM_TILE;
@@ -576,6 +666,29 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     const uint64_t dWr = make_desc(smem_u32(sm.W[0]) + WN_GATE_B, 768, 128);     // res/skip B: stage 0, hi plane
     const uint64_t dBr = make_desc(smem_u32(sm.W[0]) + WN_OFF_RBIAS, 768, 128);  // res/skip bias B: stage 0
     const uint32_t ones = tmem + WN_C_ONE;
+    uint32_t cg[WN_NT];       // consumed phases of bar_g[i] = of bar_gate[i]: one per block the tile takes part in
+#pragma unroll
+    for (int i = 0; i < WN_NT; ++i) cg[i] = 0;
+    // This warp also owns the 48 padding rows in front of row 0 (x_pad of the NEXT block, see the header): it rewrites
+    // them right after issuing rs(k, 0) - gate(k, 0), their reader, has completed by then (epilogue 1 of tile 0 ran), and
+    // the next reader, gate(k+1, 0), waits for this warp's arrival on bar_u[0] - so the copy overlaps tile 0's res/skip
+    // GEMM and epilogue 2 instead of sitting inside it (it was ~350 clk of the ~2750-clk chain of a block).
+    auto store_pad = [&](const unsigned char* chunk) {   // chunk: 64 bytes (hi0, hi1, lo0, lo1)
+      const uint4* c4 = reinterpret_cast<const uint4*>(chunk);
+      const uint4 c0 = c4[0], c1 = c4[1], c2 = c4[2], c3 = c4[3];
+#pragma unroll
+      for (int r = lane; r < WN_PAD; r += 32) {
+        unsigned char* up = sm.U + r * 16;
+        *reinterpret_cast<uint4*>(up) = c0;
+        *reinterpret_cast<uint4*>(up + WN_PU) = c1;
+        *reinterpret_cast<uint4*>(up + 2 * WN_PU) = c2;
+        *reinterpret_cast<uint4*>(up + 3 * WN_PU) = c3;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.bar_u[0]);
+    };
+    if ((int64_t)blockIdx.x < n_groups) store_pad(sm.head.pad0);   // level 0 of the first group
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
       for (int k = 0; k < 24; ++k, ++n_w) {
         const uint64_t wofs = (uint64_t)((n_w % WN_WST) * (WN_WBLK >> 4));
@@ -583,9 +696,14 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         WN_MBAR_WAIT(&sm.wfull[n_w % WN_WST], (n_w / WN_WST) & 1, 11);   // (observe the weight load ourselves)
 #pragma unroll
         for (int i = 0; i < WN_NT; ++i) {
+          if (k < P.join[i]) continue;
           if (i == 3) WN_DBG(7, k, 0);
-          WN_MBAR_WAIT(&sm.bar_g[i], n_w & 1, 10);
-          if (i < WN_NT - 1) WN_MBAR_WAIT(&sm.bar_gate[i + 1], n_w & 1, 3);
+          WN_MBAR_WAIT(&sm.bar_g[i], cg[i] & 1, 10);
+          // gate(k, i+1) reads rows of tile i that epilogue 2a of (k, i) overwrites.  cg[i+1] has not been advanced for
+          // block k yet (tile i+1 comes next in this loop), so it is the phase of gate(k, i+1)
+          if (i < WN_NT - 1 && k >= P.join[i + 1]) WN_MBAR_WAIT(&sm.bar_gate[i + 1], cg[i + 1] & 1, 3);
+          ++cg[i];
+          if (i == 0 && lane == 0) WN_DBG2(k, 13);
           if (i == 3) WN_DBG(7, k, 1);
           fence_after_sync();
           if (elect_one()) {
@@ -599,10 +717,13 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             }
             mma_f16_ts(tacc + WN_C_R, ones, bb, idesc_rs, true);
             mma_commit(&sm.bar_rs[i]);
+            if (i == 0) WN_DBG2(k, 14);
             if (i == 0) WN_DBG(5, k, 2);
             if (i == WN_NT - 1) WN_DBG(5, k, 3);
           }
           __syncwarp();
+          if (i == 0)    // padding rows of the next block (after block 23: level 0 of the next group)
+            store_pad(k < 23 ? sm.W[n_w % WN_WST] + WN_OFF_F32 + 320 : sm.head.pad0);
           if (i == 3) WN_DBG(7, k, 2);
         }
       }
@@ -719,10 +840,38 @@ __global__ void __launch_bounds__(256) wn_input_kernel(const float* __restrict__
   }
 }
 
+// Sliding-window batches share every activation outside the causal-padding cone (header): the tile schedule.
+// D(b) = rows of block b's output that depend on the window's zero padding; tile i (first time step 128*i / 3) joins
+// at the first block whose dirty prefix reaches it, from the snapshot one level below.
+struct WnSharePlan {
+  int join[WN_NT], src_slot[WN_NT], snap_slot[24], n_slots;
+};
+static WnSharePlan wn_share_plan(const int* dil, int L) {
+  WnSharePlan g;
+  for (int k = 0; k < 24; ++k) g.snap_slot[k] = -1;
+  g.n_slots = 0;
+  int D[24], acc = 0;
+  for (int k = 0; k < 24; ++k) { acc += 2 * dil[k]; D[k] = acc; }
+  for (int i = 0; i < WN_NT; ++i) {
+    const int tmin = (i * 128) / WN_G;
+    int j = 23;
+    for (int k = 0; k < 24; ++k)
+      if (D[k] > tmin) { j = k; break; }
+    if (tmin >= L) j = 23;          // no real rows in this tile: it only has to keep the barrier protocol going
+    g.join[i] = j;
+    g.src_slot[i] = -1;
+    if (j > 0 && tmin < L) {
+      if (g.snap_slot[j - 1] < 0) g.snap_slot[j - 1] = g.n_slots++;
+      g.src_slot[i] = g.snap_slot[j - 1];
+    }
+  }
+  return g;
+}
+
 int wavenet_tc_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* det_out, float* post,
                           cudaStream_t st) {
   if (wm.n_win == 0) return WWB_OK;
-  if (ctx->L > 182) return fail(ctx, WWB_ERR_ARG, "tensor-core WaveNet path supports windows up to 182 frames");
+  if (ctx->L > WN_MAXT) return fail(ctx, WWB_ERR_ARG, "tensor-core WaveNet path supports windows up to 182 frames");
   const int64_t n_rows = wm.n_streams * (int64_t)wm.ring;
   void* x0;
   int rc = workspace(ctx, 1, (size_t)std::max<int64_t>(n_rows, 1) * 16 * sizeof(float), &x0);
@@ -731,17 +880,48 @@ int wavenet_tc_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float*
       wm.mel, ctx->wn.in_w, ctx->wn.in_b, (float*)x0, n_rows);
   WWB_CHECK_LAUNCH(ctx);
   WnTcParams P;
+  memset(&P, 0, sizeof(P));
   P.x0 = (const float*)x0;
   P.wm = wm;
   P.wblob = ctx->wn.tc_blocks;
   P.head = reinterpret_cast<const WnHead*>(ctx->wn.tc_head);
   P.L = ctx->L;
   P.nsplit = ctx->precision == WWB_PREC_TC ? 3 : 1;
-  for (int b = 0; b < 24; ++b) P.dil[b] = ctx->wn.dilation[b];
-  P.enc_out = enc_out; P.det_out = det_out; P.post = post;
+  for (int b = 0; b < 24; ++b) { P.dil[b] = ctx->wn.dilation[b]; P.snap_slot[b] = -1; }
+  for (int i = 0; i < WN_NT; ++i) { P.join[i] = 0; P.src_slot[i] = -1; }
+  P.n_rows = n_rows;
   P.dbg = reinterpret_cast<long long*>(ctx->debug_buf);
   const size_t smem = sizeof(WnSmem) + 128;
   WWB_CUDA(ctx, cudaFuncSetAttribute(wavenet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+  // regular grid of >= 8 overlapping windows per stream (not the explicit lists / ring addressing of the streaming
+  // path): one stream-level pass writes the snapshots, the window groups then skip the tile-blocks that only hold
+  // shared activations
+  const char* no_share = getenv("WWB_WN_NO_SHARE");
+  const bool share = !wm.win_stream && !wm.n_win_dev && wm.b0 == 0 && wm.win_per_stream >= 8 && wm.hop < ctx->L &&
+                     !(no_share && no_share[0] == '1');
+  if (share) {
+    const WnSharePlan g = wn_share_plan(ctx->wn.dilation, ctx->L);
+    if (g.n_slots > 0) {
+      void* snap;
+      if ((rc = workspace(ctx, 2, (size_t)g.n_slots * n_rows * WN_SNAP_F * sizeof(float), &snap))) return rc;
+      WnTcParams S = P;
+      S.stream_mode = 1;
+      S.rstride = 1;
+      S.chunks_per_stream = wm.ring <= WN_ROWS ? 1 : 1 + (wm.ring - WN_ROWS + WN_CHUNK_STEP - 1) / WN_CHUNK_STEP;
+      S.snap = (float*)snap;
+      for (int b = 0; b < 24; ++b) S.snap_slot[b] = g.snap_slot[b];
+      S.enc_out = S.det_out = S.post = nullptr;
+      S.dbg = nullptr;
+      const int64_t n_chunks = wm.n_streams * (int64_t)S.chunks_per_stream;
+      wavenet_tc_kernel<<<(unsigned)std::min<int64_t>(n_chunks, ctx->sm_count), WN_THREADS, smem, st>>>(S);
+      WWB_CHECK_LAUNCH(ctx);
+      P.snap = (float*)snap;
+      for (int i = 0; i < WN_NT; ++i) { P.join[i] = g.join[i]; P.src_slot[i] = g.src_slot[i]; }
+    }
+  }
+  P.rstride = WN_G;
+  P.enc_out = enc_out; P.det_out = det_out; P.post = post;
   const int64_t n_groups = (wm.n_win + WN_G - 1) / WN_G;
   const unsigned grid = (unsigned)std::min<int64_t>(n_groups, ctx->sm_count);
   wavenet_tc_kernel<<<grid, WN_THREADS, smem, st>>>(P);
