@@ -11,9 +11,15 @@ Default workload "sweep" (BASELINE config 5, one time-chunk of it): S streams x 
 fused filter kernel -> CRNN and WaveNet encode+detect over all hop-2 windows
 (get_posterior semantics) -> FAR/FRR counters.  Per-GPU work is fixed (weak scaling);
 streams shard over ranks and the only collective is one all-reduce of the int64 counters.
+Every step sees different PCM (three rotating batches from counter-based seeds, a wake clip
+spliced into some streams so that the counters are not all zero).
 `value` = audio-hours of PCM all ranks processed per second with the PCM resident in
-HBM; `e2e` = same with the PCM in pinned host memory, H2D + D2H of the posteriors and
-counters inside the timed region.  Prints ONE JSON line on rank 0.
+HBM; `e2e` = the same work through the library's host-buffer plugin call
+(wwb_sweep_submit / wwb_sweep_wait over ctypes, numpy buffers in pinned host memory): H2D of
+the PCM, kernels, D2H of the posteriors and counters, all inside the timed region.
+`extra.parity` compares a sample of the step's posteriors / decisions / counters with the CPU
+oracle (outside the timed region); `extra.configs` carries short measurements of BASELINE
+configs 2, 3 and 4.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -151,6 +157,12 @@ def workload_models(workload):
     return {"sweep": ["CRNN", "Wavenet"], "crnn": ["CRNN"], "wavenet": ["Wavenet"], "filter": []}[workload]
 
 
+def default_shape(workload, args):
+    if workload == "filter":
+        return args.streams or 100000, int((args.seconds or 2.0) * 16000)       # BASELINE config 2
+    return args.streams or 2560, int((args.seconds or 10.0) * 16000)            # one time-chunk of config 5 per GPU
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -168,11 +180,13 @@ def run_reference_arm(args):
             rates.append((r, dt))
     value = float(np.mean([r for r, _ in rates]))
     ms = float(np.mean([dt for _, dt in rates]) * 1e3)
-    sample = "%d streams x %.0f s per step, %d processes x 1 thread, numpy restatement of the TFLite graphs" % (cores, sec, cores)
+    sample = ("each step a bounded sample of the workload: %d streams x %.0f s, %d processes x 1 thread, numpy restatement "
+              "of the TFLite graphs (TFLite itself is not installable here)" % (cores, sec, cores))
+    S, N = default_shape(args.workload, args)
     line = {"impl": "reference", "metric": "audio_hours_per_sec", "value": value, "unit": "audio-h/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": config_dict(args, None, None),
+            "data": "synthetic", "config": config_dict(args, S, N),
             "cpu_baseline": {"value": value, "unit": "audio-h/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "audio-h/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -215,10 +229,189 @@ def config_dict(args, S, N):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa_node(torch, local):
+    """Pins this process (and so its page-locked buffers, first-touch) to the NUMA node of its GPU: with eight ranks
+    feeding eight GPUs the host->device copies otherwise cross the socket interconnect."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+def make_pcm(synth, wake, S, N, seed, dev, first_stream):
+    """One batch of device-generated PCM with the wake clip of every model spliced into a few streams."""
+    import torch
+    pcm = synth.device_pcm(S, N, seed=seed, device=dev, first_stream=first_stream)
+    k = 0
+    for sidx in sorted({0, S // 3, S // 2, S - 1}):
+        for name, clip in wake.items():
+            at = (k * 16000) % max(1, N - clip.numel())
+            n = min(clip.numel(), N - at)
+            if sidx + (0 if name == "crnn" else 1) < S and n > 0:
+                pcm[sidx + (0 if name == "crnn" else 1), at:at + n] = clip[:n]
+            k += 1
+    return pcm
+
+
+def parity_report(engines, models, pcm, post, thr, S):
+    """extra.parity: the step's posteriors, decisions and counters against the CPU oracle on streams that carry wake
+    clips and on a noise stream (outside the timed region; oracle = numpy restatement of the TFLite graphs)."""
+    from oracle import restated as R
+    out = {"windows_checked": 0, "max_abs_err": 0.0, "decision_flips_outside_band": 0, "decisions_fired": 0,
+           "counters_equal": True, "counter_thresholds_differing": 0, "tolerance": 1e-3, "streams": []}
+    streams = sorted({0, 1, S // 2, S // 2 + 1, 2})[:4]
+    out["streams"] = streams
+    for m in models:
+        e = engines[m]
+        w = e.weights
+        L = int(w["mel_length"])
+        ref_rows = []
+        for sidx in streams:
+            mel = R.mel_stream(R.int16_to_float(pcm[sidx].cpu().numpy()), w)
+            j = np.arange(R.eval_windows(mel.shape[0], L))
+            ref = R.posterior(mel[(2 * j)[:, None] + np.arange(L)[None, :]], w).astype(np.float32)
+            got = post[m][sidx].cpu().numpy()
+            err = np.abs(got - ref)
+            band = np.abs(ref - 0.5) <= 1e-3
+            out["windows_checked"] += int(j.size)
+            out["max_abs_err"] = max(out["max_abs_err"], float(err.max()))
+            out["decision_flips_outside_band"] += int(((got > 0.5) != (ref > 0.5))[~band].sum())
+            out["decisions_fired"] += int((ref > 0.5).sum())
+            ref_rows.append(ref)
+        # counters of the checked streams: GPU kernel on the GPU posteriors vs the oracle's loops on the oracle posteriors
+        sub = np.stack([post[m][sidx].cpu().numpy() for sidx in streams])
+        seg = np.arange(len(streams) + 1, dtype=np.int64) * sub.shape[1]
+        far = e.eval_counts(sub, seg, thr, "far_edges").cpu().numpy()
+        frr = e.eval_counts(sub, seg, thr, "frr_max").cpu().numpy()
+        far_ref = sum(np.array([R.rising_edges(R.smooth_same(r), t) for t in thr]) for r in ref_rows)
+        frr_ref = np.array([sum(1 for r in ref_rows if r.max() > t) for t in thr])
+        diff = int((far != far_ref).sum() + (frr != frr_ref).sum())
+        out["counter_thresholds_differing"] += diff
+        out["counters_equal"] = out["counters_equal"] and diff == 0
+        out[m + "_far_edges_at_0.5"] = int(far[0])
+        out[m + "_accepts_at_0.5"] = int(frr[0])
+    return out
+
+
+def extra_configs(torch, engines, dev, pk, precision):
+    """Short measurements of BASELINE configs 2, 3 and 4 (CUDA events, inputs resident, >= 3 warm-up passes)."""
+    from wakeword_detection_b200 import synth
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    out = {}
+
+    def timed(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    crnn, wn = engines.get("CRNN"), engines.get("Wavenet")
+    first = crnn or wn
+    # config 2: mel filterbank extraction only, 100 000 clips x 2 s (6.4 GB of int16 PCM: larger than L2)
+    S2, N2 = 100000, 32000
+    pcm = synth.device_pcm(S2, N2, seed=77, device=dev)
+    F2 = first.num_frames(N2)
+    mel = torch.empty((S2, F2, 40), dtype=torch.float32, device=dev)
+    ms = timed(lambda: first.filter(pcm, 0.0, out=mel), 5)
+    gbs = S2 * F2 * BYTES_PER_FRAME / (ms / 1e3) / 1e9
+    out["config2_filter"] = {"workload": "100000 clips x 2 s, mel extraction only", "ms_per_step": ms,
+                             "audio_h_per_s": S2 * N2 / 16000.0 / 3600.0 / (ms / 1e3),
+                             "roofline": {"bound": "hbm", "kernel": "filter_kernel", "achieved": gbs, "peak": pk["hbm_gbs"],
+                                          "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]},
+                             "l2": "inputs larger than L2"}
+    del pcm, mel
+    torch.cuda.empty_cache()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if crnn is not None:
+        # config 3: 8192 independent [151, 40] windows per launch (per-window tiles: nothing is shared between windows)
+        pcm3 = synth.device_pcm(64, 160 * 300 + 512, seed=3, device=dev)
+        m3 = crnn.filter(pcm3)
+        wins = m3.unfold(1, 151, 1).permute(0, 1, 3, 2)[:, :128].reshape(-1, 151, 40).contiguous()
+        post3 = torch.empty((8192, 1), dtype=torch.float32, device=dev)
+
+        def c3():
+            flush.fill_(1)
+            crnn.posteriors(wins, 1, out=post3)
+        ms_all = timed(c3, 10)
+        ms_flush = timed(lambda: flush.fill_(1), 10)
+        ms = ms_all - ms_flush
+        tf = 8192 * FLOP_PER_WINDOW["CRNN"] / (ms / 1e3) / 1e12
+        out["config3_crnn_windows"] = {"workload": "8192 independent CRNN windows (wwb_posteriors, n_frames == L)", "ms_per_step": ms,
+                                       "windows_per_s": 8192 / (ms / 1e3),
+                                       "roofline": {"bound": "tensor", "kernel": "crnn encode+detect", "achieved": tf,
+                                                    "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                                    "frac": tf / pk["bf16_tflops_sustained"]},
+                                       "l2": "flushed between steps (flush time subtracted)"}
+    if wn is not None:
+        # config 4: 4096 concurrent streams, every push brings 160 samples = one new mel frame per stream (hop 1) and
+        # re-scores the stream's [182, 40] ring window; state (PCM tail, mel ring, posterior max) lives in HBM
+        from wakeword_detection_b200 import _cabi
+        e4 = _cabi.Engine(wn.weights, dev.index, precision)
+        S4 = 4096
+        e4.stream_alloc(S4, 160)
+        pcm4 = synth.device_pcm(S4, 160 * 64, seed=9, device=dev)
+        chunks = [pcm4[:, i * 160:(i + 1) * 160].contiguous() for i in range(64)]
+        for c in chunks[:8]:
+            e4.stream_push(c)
+        state = {"i": 8}
+
+        def c4():
+            e4.stream_push(chunks[state["i"] % 64])
+            state["i"] += 1
+        ms = timed(c4, 48, warm=4)
+        tf = S4 * FLOP_PER_WINDOW["Wavenet"] / (ms / 1e3) / 1e12
+        out["config4_wavenet_streaming"] = {"workload": "4096 streams x 1 new frame per wwb_stream_push (hop 1)", "ms_per_step": ms,
+                                            "pushes_per_s": 1e3 / ms, "stream_steps_per_s": S4 * 1e3 / ms,
+                                            "audio_h_per_s": S4 * 0.01 / 3600.0 / (ms / 1e3),
+                                            "roofline": {"bound": "tensor", "kernel": "wavenet encode+detect", "achieved": tf,
+                                                         "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                                         "frac": tf / pk["bf16_tflops_sustained"]},
+                                            "l2": "working set 119 MB of mel rings + per-push PCM; no flush (streaming state is meant to stay hot)"}
+        e4.close()
+    return out
+
+
+def cpu_config1_leg():
+    """SURVEY 8(d) config 1, faithful call pattern: one 10 s stream pushed as 500 chunks of 320 samples through the
+    WakewordTrigger state machine of the oracle, CRNN, batch 1, one thread: 997 mel frames -> 997 encode + detect."""
+    from threadpoolctl import threadpool_limits
+    from oracle import restated as R
+    from wakeword_detection_b200 import synth, weights as W
+    w = W.load_model_dir(os.path.join(ROOT, "weights", "CRNN"), "CRNN")
+    pcm = synth.stream_int16(160000, 2, 11, 0)
+    with threadpool_limits(limits=1):
+        trig = R.TriggerOracle(w, threshold=2.0)
+        t0 = time.perf_counter()
+        for i in range(500):
+            trig(pcm[i * 320:(i + 1) * 320], True)
+        dt = time.perf_counter() - t0
+    return {"audio_h_per_s": 10.0 / 3600.0 / dt, "seconds": dt, "invokes": len(trig.posteriors), "cores": 1, "kind": "port",
+            "sample": "config 1: one 10 s stream, 500 x 320-sample frames through the trigger state machine, CRNN, batch 1"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sweep", choices=["sweep", "filter", "crnn", "wavenet"])
@@ -226,8 +419,10 @@ def main():
     ap.add_argument("--seconds", type=float, default=0.0, help="seconds per stream (0 = workload default)")
     ap.add_argument("--precision", default="tc", choices=["f32", "tc", "tc_fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra.configs / extra.parity (kernel work only)")
     args = ap.parse_args()
     if args.warmup < 3:
+        sys.stderr.write("bench.py: --warmup %d is below the 3 warm-up steps the timing rules require; using 3\n" % args.warmup)
         args.warmup = 3
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -243,39 +438,31 @@ def main():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
     models = workload_models(args.workload)
-    if args.workload == "filter":
-        S, N = args.streams or 100000, int((args.seconds or 2.0) * 16000)       # BASELINE config 2
-    else:
-        S, N = args.streams or 512, int((args.seconds or 10.0) * 16000)
+    S, N = default_shape(args.workload, args)
     engines = {m: _cabi.Engine(W.load_model_dir(os.path.join(ROOT, "weights", m), m), local, args.precision)
                for m in (models or ["CRNN"])}
     first = next(iter(engines.values()))
     F = first.num_frames(N)
     nwin = {m: e.num_windows(F, 2) for m, e in engines.items()} if models else {}
 
-    pcm_dev = synth.device_pcm(S, N, seed=1234, device=dev, first_stream=rank * S)
-    pcm_host = torch.empty((S, N), dtype=torch.int16).pin_memory()
-    pcm_host.copy_(pcm_dev)
-    pcm_stage = torch.empty_like(pcm_dev)
+    # three rotating batches: every step sees different PCM; wake clips make the counters non-zero
+    wake = {k: torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "wake_%s_pcm.npy" % k))).to(dev)
+            for k in ("crnn", "wavenet")} if models else {}
+    NB = 3 if S * N * 2 <= 2e9 else 1
+    pcm_dev = [make_pcm(synth, wake, S, N, 1234 + 7919 * i, dev, rank * S) for i in range(NB)]
     mel = torch.empty((S, F, 40), dtype=torch.float32, device=dev)
     post = {m: torch.empty((S, nwin[m]), dtype=torch.float32, device=dev) for m in models}
-    post_host = {m: torch.empty((S, nwin[m]), dtype=torch.float32).pin_memory() for m in models}
     thr = np.arange(0.5, 0.99999, 0.005)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if S * N * 2 <= 126e6 else None
     stage_ms = {"filter": 0.0, **{m: 0.0 for m in models}, "counts": 0.0}
     ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def counts():
-        counters = []
-        for m in models:
-            seg = np.arange(S + 1, dtype=np.int64) * nwin[m]
-            counters.append(engines[m].eval_counts(post[m], seg, thr, "far_edges"))
-            counters.append(engines[m].eval_counts(post[m], seg, thr, "frr_max"))
-        return counters
+    step_no = {"i": 0}
+    seg = {m: np.arange(S + 1, dtype=np.int64) * nwin[m] for m in models}
 
     def step(src, timed_stages=None):
         marks = [ev()]
@@ -287,9 +474,8 @@ def main():
             engines[m].posteriors(mel, 2, out=post[m])
             marks.append(ev()); marks[-1].record()
         for m in models:
-            seg = np.arange(S + 1, dtype=np.int64) * nwin[m]
-            counters.append(engines[m].eval_counts(post[m], seg, thr, "far_edges"))
-            counters.append(engines[m].eval_counts(post[m], seg, thr, "frr_max"))
+            counters.append(engines[m].eval_counts(post[m], seg[m], thr, "far_edges"))
+            counters.append(engines[m].eval_counts(post[m], seg[m], thr, "frr_max"))
         marks.append(ev()); marks[-1].record()
         if timed_stages is not None:
             timed_stages.append(marks)
@@ -313,55 +499,16 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    last_counters = {}
+
     def dev_step(stages=None):
         if flush is not None:
             flush.fill_(1)
-        c = step(pcm_dev, stages)
-        if world > 1 and c:
-            wdist.all_reduce_counters(*c)
-
-    # End to end: the streams are pushed through in E2E_CHUNKS slices; the host->device copy of slice i+1 (copy stream)
-    # overlaps filter -> encode -> detect of slice i (compute stream), as a caller feeding host buffers would do it.
-    # Three slices growing geometrically (g, 2g, rest; g = the engines' stream granule, i.e. whole waves of the persistent
-    # kernels): the first copy is the only one nothing can hide, so it is small, and each later copy is finished long
-    # before the kernels of the slices in front of it are (measured: 27.14 ms against 27.44 ms for g / 4g / 4g / rest).
-    gran = max([e.stream_granule(F, 2) for e in engines.values()] or [1])
-    if gran > 1 and S >= 4 * gran:
-        bounds = [0, gran, 3 * gran, S]
-    elif S >= 8:
-        bounds = [S * i // 4 for i in range(5)]      # no granule (filter-only workloads are copy-bound): four equal slices
-    else:
-        bounds = [0, S]
-    if os.environ.get("WWB_E2E_BOUNDS"):
-        bounds = [int(x) for x in os.environ["WWB_E2E_BOUNDS"].split(",")]
-    E2E_CHUNKS = len(bounds) - 1
-    copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event() for _ in range(E2E_CHUNKS)]
-
-    def e2e_step():
-        main = torch.cuda.current_stream(dev)
-        copy_stream.wait_stream(main)          # the staging buffer of the previous step is free
-        with torch.cuda.stream(copy_stream):
-            for i in range(E2E_CHUNKS):
-                sl = slice(bounds[i], bounds[i + 1])
-                pcm_stage[sl].copy_(pcm_host[sl], non_blocking=True)
-                copied[i].record(copy_stream)
-        for i in range(E2E_CHUNKS):
-            main.wait_event(copied[i])
-            sl = slice(bounds[i], bounds[i + 1])
-            first.filter(pcm_stage[sl], 0.0, out=mel[sl])
-            for m in models:
-                engines[m].posteriors(mel[sl], 2, out=post[m][sl])
-        c = counts()
+        c = step(pcm_dev[step_no["i"] % NB], stages)
+        step_no["i"] += 1
         if world > 1 and c:
             c = wdist.all_reduce_counters(*c)
-        for m in models:
-            post_host[m].copy_(post[m], non_blocking=True)
-        if c:
-            torch.stack(list(c)).cpu()
-        else:
-            mel[:, :1].cpu()
-        torch.cuda.synchronize()
+        last_counters["c"] = c
 
     for _ in range(args.warmup):
         dev_step()
@@ -390,11 +537,77 @@ def main():
     ms_per_step = (total_ms - flush_ms) / args.steps
     audio_h = world * S * N / 16000.0 / 3600.0
     value = audio_h / (ms_per_step / 1e3)
+    counters_dev = [int(x) for c in (last_counters.get("c") or []) for x in (c[0].item(), c[-1].item())]
 
-    for _ in range(2):
-        e2e_step()
-    e2e_ms = timed(e2e_step, args.steps) / args.steps
-    e2e_value = audio_h / (e2e_ms / 1e3)
+    # ---------------- end to end through the host-buffer plugin call ----------------
+    # PCM in page-locked numpy buffers (two, rotating) -> wwb_sweep_submit (ONE H2D copy + ONE filter pass feed every
+    # model; two jobs in flight, so the copy of step k+1 overlaps the kernels of step k) -> wwb_sweep_wait (posteriors and
+    # counters in host memory).  Timed with the host clock around the synchronous calls, barrier + device sync on both sides.
+    elist = [engines[m] for m in models] or [first]
+    e2e = None
+    if models:
+        host_pcm = []
+        for i in range(2):
+            h = _cabi.pinned_empty((S, N), np.int16)
+            torch.from_numpy(h).copy_(pcm_dev[i % NB])
+            host_pcm.append(h)
+        recs = [None, None]
+
+        def submit(i):
+            recs[i % 2] = elist[0].sweep_submit(host_pcm[i % 2], 2, thr, others=elist[1:], out=recs[i % 2])
+
+        def finish(i):
+            elist[0].sweep_wait()
+            r = recs[i % 2]
+            if world > 1:
+                t = torch.from_numpy(np.stack(r["far"] + r["frr"])).to(dev)
+                dist.all_reduce(t)
+                t.cpu()
+            return r
+
+        def e2e_run(steps):
+            submit(0)
+            for i in range(1, steps):
+                submit(i)
+                finish(i - 1)
+            return finish(steps - 1)
+
+        e2e_run(3)
+        sync_all()
+        t0 = time.perf_counter()
+        last = e2e_run(args.steps)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(dt.item()) * 1e3 / args.steps
+        h2d = S * N * 2
+        d2h = sum(S * nwin[m] * 4 for m in models) + len(models) * 2 * thr.size * 8
+        # the host-call results of the last step equal the resident path's on the same PCM (same kernels)
+        chk = step(pcm_dev[(args.steps - 1) % 2 % NB])
+        torch.cuda.synchronize()
+        same = all(np.array_equal(last["post"][k], post[m].cpu().numpy()) for k, m in enumerate(models))
+        same = same and all(np.array_equal(last["far"][k], chk[2 * k].cpu().numpy()) and
+                            np.array_equal(last["frr"][k], chk[2 * k + 1].cpu().numpy()) for k in range(len(models)))
+        e2e = {"value": audio_h / (e2e_ms / 1e3), "unit": "audio-h/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_ms, "api": "wwb_sweep_submit / wwb_sweep_wait (C ABI over ctypes, numpy host buffers, pinned)",
+               "timer": "host clock around the synchronous calls, barrier + device sync on both sides, max over ranks",
+               "equals_resident_path": bool(same), "numa_node": numa}
+    else:
+        # filter only: host PCM -> H2D -> filter -> first mel rows back (copy-bound: 6.4 GB of PCM per step)
+        host = _cabi.pinned_empty((S, N), np.int16)
+        torch.from_numpy(host).copy_(pcm_dev[0])
+        stage = torch.empty_like(pcm_dev[0])
+        th = torch.from_numpy(host)
+
+        def fstep():
+            stage.copy_(th, non_blocking=True)
+            first.filter(stage, 0.0, out=mel)
+            mel[:, :1].cpu()
+        fstep()
+        e2e_ms = timed(fstep, args.steps) / args.steps
+        e2e = {"value": audio_h / (e2e_ms / 1e3), "unit": "audio-h/s", "h2d_bytes_per_step": S * N * 2,
+               "d2h_bytes_per_step": S * 160, "ms_per_step": e2e_ms, "api": "Engine.filter on a staged copy", "numa_node": numa}
 
     pk, pk_src = peaks()
     per = {k: v / args.steps for k, v in stage_ms.items()}
@@ -411,7 +624,9 @@ def main():
     roof["peak_source"] = pk_src + (" (sustained bf16)" if dom != "filter" else " (copy)")
     extra = {"ms_per_stage": per,
              "filter_GBps": S * F * BYTES_PER_FRAME / (per["filter"] / 1e3) / 1e9,
-             "filter_frac_of_hbm": S * F * BYTES_PER_FRAME / (per["filter"] / 1e3) / 1e9 / pk["hbm_gbs"]}
+             "filter_frac_of_hbm": S * F * BYTES_PER_FRAME / (per["filter"] / 1e3) / 1e9 / pk["hbm_gbs"],
+             "pcm": "%d rotating device batches (counter-based seeds), wake clips spliced into 8 streams of each" % NB,
+             "counters_first_last_threshold": counters_dev}
     for m in models:
         tf = S * nwin[m] * FLOP_PER_WINDOW[m] / (per[m] / 1e3) / 1e12
         extra[m + "_TFLOPs"] = tf
@@ -427,6 +642,22 @@ def main():
         extra["CRNN_shared_columns"] = {"executed_flop_per_window": exe,
                                         "executed_TFLOPs": S * nwin["CRNN"] * exe / (per["CRNN"] / 1e3) / 1e12,
                                         "columns_per_window": cols / nwin["CRNN"]}
+    if "Wavenet" in models and args.precision != "f32" and nwin["Wavenet"] >= 8:
+        # Sliding windows take every activation outside the causal-padding cone from a stream-level pass
+        # (wavenet_tc.cu): 62 of 120 tile-blocks per group of 3 windows + 24 blocks per 460 stream frames are executed.
+        frac = 62.0 / 120.0 + (F / 460.0) * 120.0 / (nwin["Wavenet"] / 3.0 * 120.0)
+        exe = FLOP_PER_WINDOW["Wavenet"] * frac
+        extra["Wavenet_shared_activations"] = {"executed_fraction_of_tile_blocks": frac,
+                                               "executed_TFLOPs": S * nwin["Wavenet"] * exe / (per["Wavenet"] / 1e3) / 1e12}
+
+    if rank == 0 and models and not args.no_extras:
+        dev_step()
+        torch.cuda.synchronize()
+        extra["parity"] = parity_report(engines, models, pcm_dev[(step_no["i"] - 1) % NB], post, thr, S)
+    if rank == 0 and not args.no_extras and args.workload == "sweep":
+        del pcm_dev
+        torch.cuda.empty_cache()
+        extra["configs"] = extra_configs(torch, engines, dev, pk, args.precision)
 
     if rank == 0:
         cpu = None
@@ -442,17 +673,16 @@ def main():
                 cpu = {"value": r, "unit": "audio-h/s", "cores": 1, "kind": "port",
                        "sample": "1 stream x %.0f s through %s, numpy restatement of the TFLite graphs, 1 thread (%.1f s)"
                                  % (sec, "+".join(cm), dt)}
-        h2d = S * N * 2
-        d2h = sum(S * nwin[m] * 4 for m in models) + len(models) * 2 * thr.size * 8
+                if not args.no_extras:
+                    extra["cpu_config1_batch1"] = cpu_config1_leg()
         line = {"metric": "audio_hours_per_sec", "value": value, "unit": "audio-h/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "f32" else "f16x2->f32",
                 "data": "synthetic", "config": config_dict(args, S, N), "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "audio-h/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "extra": extra}
+                "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "extra": extra}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -151,9 +151,29 @@ int wwb_posteriors(wwb_ctx* ctx, const float* mel_dev, int64_t n_streams, int64_
 int wwb_pipeline(wwb_ctx* ctx, const void* pcm_dev, int pcm_dtype, int64_t n_streams,
                  int64_t n_samples, int64_t pitch_samples, float pre_emphasis, int hop,
                  float* post_dev, void* stream);
-/* same through HOST buffers: H2D of the PCM, kernels, D2H of the posteriors, sync. */
+/* same through HOST buffers - the call that replaces TFLiteModel.__call__'s copy-in / invoke /
+ * copy-out (spokestack/models/tensorflow.py:33-51) for a batch of streams: H2D of the PCM in
+ * three slices overlapped with the kernels, D2H of the posteriors, sync.  Host buffers that
+ * are not page-locked are registered on first use (cached per address range). */
 int wwb_pipeline_host(wwb_ctx* ctx, const void* pcm_host, int pcm_dtype, int64_t n_streams,
                       int64_t n_samples, float pre_emphasis, int hop, float* post_host);
+/* Asynchronous form for sweeps (utils/evaluate_models.py:280-327 runs both model types over
+ * the same audio): ONE host->device copy and ONE filter pass feed n_ctx models (ctxs[0] runs
+ * the filter and owns the pipeline; all ctxs on one device).  Per model m: posteriors
+ * post_host[m] [n_streams, n_win_m] and, if thr_host != NULL, the FAR rising-edge counts
+ * (every stream one trajectory, 30-tap smoothing) and the FRR per-stream-max counts
+ * (evaluate_models.py:183-218) as int64 [n_thr] each; any output pointer may be NULL.
+ * Returns once the work is enqueued; up to two jobs may be in flight (the copy of job k+1
+ * overlaps the kernels of job k).  wwb_sweep_wait blocks until the OLDEST job's results
+ * are in host memory.  Input and output buffers must stay valid until then. */
+int wwb_sweep_submit(wwb_ctx* const* ctxs, int n_ctx, const void* pcm_host, int pcm_dtype,
+                     int64_t n_streams, int64_t n_samples, float pre_emphasis, int hop,
+                     const double* thr_host, int n_thr, float* const* post_host,
+                     int64_t* const* far_counts_host, int64_t* const* frr_counts_host);
+int wwb_sweep_wait(wwb_ctx* ctx0);
+/* page-locked host memory for the *_host entry points (cudaHostAlloc / cudaFreeHost) */
+int wwb_host_alloc(void** out, size_t bytes);
+int wwb_host_free(void* p);
 
 /* FAR/FRR numerators (evaluate_models.py:183-218, plot_eval_models.py:84-129).
  * post[seg_off[i] : seg_off[i+1]] is segment i (clip or trajectory).

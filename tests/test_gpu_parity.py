@@ -295,6 +295,47 @@ def test_pipeline_device_and_host(wname, name, wake_pcm):
     assert post[0].max() > 0.9 and post[1].max() < 0.5
 
 
+def test_sweep_host_pipeline_two_jobs_in_flight(wake_pcm):
+    """wwb_sweep_submit / wwb_sweep_wait: host PCM -> ONE copy + ONE filter pass -> CRNN and WaveNet posteriors and the
+    FAR / FRR counters in host memory; two jobs in flight.  Results equal the device-buffer path bit for bit, and the
+    synchronous wwb_pipeline_host accepts pageable numpy buffers."""
+    from wakeword_detection_b200 import _cabi
+    crnn, wn = get_engine("CRNN"), get_engine("Wavenet")
+    S, N = 70, 64000
+    thr = R.thresholds_eval()
+    jobs = []
+    for j in range(3):
+        pcm = _cabi.pinned_empty((S, N), np.int16)
+        pcm[:] = synth.batch_int16(S, N, seed=40 + j)
+        pcm[j, 1000:1000 + 35200] = wake_pcm["crnn"]
+        pcm[j + 5, 20000:20000 + 35200] = wake_pcm["wavenet"]
+        jobs.append(pcm)
+    recs = [crnn.sweep_submit(jobs[0], 2, thr, others=[wn]), crnn.sweep_submit(jobs[1], 2, thr, others=[wn])]
+    with pytest.raises(IndexError):
+        crnn.sweep_submit(jobs[2], 2, thr, others=[wn])              # two jobs are in flight already
+    crnn.sweep_wait()
+    recs.append(crnn.sweep_submit(jobs[2], 2, thr, others=[wn]))
+    crnn.sweep_wait()
+    crnn.sweep_wait()
+    with pytest.raises(IndexError):
+        crnn.sweep_wait()
+    for pcm, rec in zip(jobs, recs):
+        for m, eng in enumerate((crnn, wn)):
+            post = eng.pipeline(pcm.copy(), hop=2)
+            np.testing.assert_array_equal(rec["post"][m], post.cpu().numpy())
+            seg = np.arange(S + 1) * post.shape[1]
+            np.testing.assert_array_equal(rec["far"][m], eng.eval_counts(post, seg, thr, "far_edges").cpu().numpy())
+            np.testing.assert_array_equal(rec["frr"][m], eng.eval_counts(post, seg, thr, "frr_max").cpu().numpy())
+            assert rec["frr"][m][0] >= 1                              # the spliced clip fires its model
+    # synchronous single-model call, pageable input and output
+    pageable = np.array(jobs[0])
+    out = wn.pipeline_host(pageable, hop=2)
+    np.testing.assert_array_equal(out, recs[0]["post"][1])
+    small = crnn.pipeline_host(pageable[:3, :16000], hop=2)
+    np.testing.assert_array_equal(small, crnn.pipeline(pageable[:3, :16000].copy(), hop=2).cpu().numpy())
+    assert crnn.pipeline_host(np.zeros((2, 400), np.int16), hop=2).shape == (2, 0)
+
+
 def test_crnn_batch_config3_properties():
     """config 3 shape: 8192 windows in one launch; the batch a window sits in must not
     change its result, and window order is preserved."""

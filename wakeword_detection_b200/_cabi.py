@@ -58,6 +58,11 @@ PROTOTYPES = {
     "wwb_posteriors": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp, _vp]),
     "wwb_pipeline": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, C.c_float, C.c_int, _vp, _vp]),
     "wwb_pipeline_host": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, C.c_float, C.c_int, _vp]),
+    "wwb_sweep_submit": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, C.c_int, _i64, _i64, C.c_float, C.c_int, _vp, C.c_int,
+                                   C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "wwb_sweep_wait": (C.c_int, [_vp]),
+    "wwb_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
+    "wwb_host_free": (C.c_int, [_vp]),
     "wwb_eval_counts": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "wwb_stream_alloc": (C.c_int, [_vp, _i64, _i64]),
     "wwb_stream_push": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp]),
@@ -94,6 +99,23 @@ def load_library() -> C.CDLL:
 
 class WwbError(RuntimeError):
     pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array over page-locked host memory from wwb_host_alloc (freed when the array is collected): the
+    host-buffer entry points copy from / to such arrays without the driver's pageable staging."""
+    import weakref
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = _vp()
+    rc = lib.wwb_host_alloc(C.byref(p), max(n, 16))
+    if rc:
+        raise WwbError((lib.wwb_last_error(None) or b"").decode())
+    buf = (C.c_char * max(n, 16)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.wwb_host_free, p.value)
+    return arr
 
 
 def _raise(code: int, msg: str):
@@ -335,6 +357,52 @@ class Engine:
         self._check(self.lib.wwb_pipeline_host(self.ctx, pcm.ctypes.data, dt, S, N, float(pre_emphasis), int(hop),
                                                post.ctypes.data))
         return post
+
+    def sweep_submit(self, pcm: np.ndarray, hop: int = 2, thresholds=None, others: Sequence["Engine"] = (),
+                     pre_emphasis: float = 0.0, want_post: bool = True, out=None):
+        """Asynchronous host-buffer pipeline (wwb_sweep_submit): `pcm` [S, N] numpy (ideally from `pinned_empty`) ->
+        for this engine and every engine in `others` (same device; ONE copy and ONE filter pass feed all of them)
+        posteriors [S, n_win] and, with `thresholds`, the FAR-edge / FRR-max counters, all in HOST memory once
+        `sweep_wait()` returns.  Returns the result record (dict of numpy arrays) that the wait fills."""
+        if pcm.ndim != 2 or not pcm.flags.c_contiguous:
+            raise ValueError("PCM must be a C-contiguous [n_streams, n_samples] array")
+        if pcm.dtype == np.int16:
+            dt = WWB_PCM_I16
+        elif pcm.dtype == np.float32:
+            dt = WWB_PCM_F32
+        else:
+            raise ValueError("PCM must be int16 or float32")
+        engines = [self] + list(others)
+        S, N = pcm.shape
+        F = self.num_frames(N)
+        n = len(engines)
+        rec = out if out is not None else {"post": [None] * n, "far": [None] * n, "frr": [None] * n}
+        thr = None
+        if thresholds is not None:
+            thr = np.ascontiguousarray(thresholds, np.float64)
+            if thr.ndim != 1 or thr.size == 0 or np.any(np.diff(thr) < 0):
+                raise ValueError("thresholds must be a non-empty ascending 1-D array")
+        for m, e in enumerate(engines):
+            nw = e.num_windows(F, hop)
+            if want_post and (rec["post"][m] is None or rec["post"][m].shape != (S, nw)):
+                rec["post"][m] = pinned_empty((S, nw), np.float32)
+            if thr is not None:
+                for k in ("far", "frr"):
+                    if rec[k][m] is None or rec[k][m].shape != (thr.size,):
+                        rec[k][m] = np.zeros((thr.size,), np.int64)
+        arr = lambda xs: (_vp * n)(*[(x.ctypes.data if x is not None else None) for x in xs])
+        ctxs = (_vp * n)(*[e.ctx for e in engines])
+        self._check(self.lib.wwb_sweep_submit(
+            ctxs, n, pcm.ctypes.data, dt, S, N, float(pre_emphasis), int(hop),
+            thr.ctypes.data if thr is not None else None, int(thr.size) if thr is not None else 0,
+            arr(rec["post"]) if want_post else None, arr(rec["far"]) if thr is not None else None,
+            arr(rec["frr"]) if thr is not None else None))
+        rec["_keep"] = (pcm, thr)
+        return rec
+
+    def sweep_wait(self) -> None:
+        """Blocks until the oldest submitted job's results are in host memory."""
+        self._check(self.lib.wwb_sweep_wait(self.ctx))
 
     def _cached_const(self, kind: str, arr: np.ndarray):
         """Device copy of a small host array (segment offsets, threshold grids), reused while its content is unchanged:

@@ -309,6 +309,7 @@ int wwb_destroy(wwb_ctx* ctx) {
   if (!ctx) return WWB_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  host_pipe_destroy(ctx);
   for (void* p : ctx->owned) cudaFree(p);
   for (int i = 0; i < 8; ++i)
     if (ctx->ws[i]) cudaFree(ctx->ws[i]);
@@ -416,26 +417,6 @@ int wwb_pipeline(wwb_ctx* ctx, const void* pcm, int dtype, int64_t S, int64_t N,
   if (rc) return rc;
   if ((rc = wwb_filter(ctx, pcm, dtype, S, N, pitch, a, (float*)mel, stream))) return rc;
   return wwb_posteriors(ctx, (const float*)mel, S, F, hop, post, stream);
-}
-
-int wwb_pipeline_host(wwb_ctx* ctx, const void* pcm_host, int dtype, int64_t S, int64_t N, float a, int hop,
-                      float* post_host) {
-  if (!ctx) return WWB_ERR_ARG;
-  if (dtype != WWB_PCM_I16 && dtype != WWB_PCM_F32) return fail(ctx, WWB_ERR_ARG, "bad pcm dtype");
-  WWB_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t esz = dtype == WWB_PCM_I16 ? 2 : 4;
-  const int64_t F = wwb_num_frames(N);
-  const int64_t nwin = S * wwb_num_windows(ctx, F, hop);
-  void *dpcm, *dpost;
-  int rc;
-  if ((rc = workspace(ctx, 6, (size_t)S * N * esz, &dpcm))) return rc;
-  if ((rc = workspace(ctx, 7, (size_t)std::max<int64_t>(nwin, 1) * sizeof(float), &dpost))) return rc;
-  cudaStream_t st = 0;
-  if (S * N > 0) WWB_CUDA(ctx, cudaMemcpyAsync(dpcm, pcm_host, (size_t)S * N * esz, cudaMemcpyHostToDevice, st));
-  if ((rc = wwb_pipeline(ctx, dpcm, dtype, S, N, N, a, hop, (float*)dpost, st))) return rc;
-  if (nwin > 0) WWB_CUDA(ctx, cudaMemcpyAsync(post_host, dpost, (size_t)nwin * sizeof(float), cudaMemcpyDeviceToHost, st));
-  WWB_CUDA(ctx, cudaStreamSynchronize(st));
-  return WWB_OK;
 }
 
 int wwb_eval_counts(wwb_ctx* ctx, const float* post, const int64_t* seg_off, int64_t n_seg, const int32_t* halo_lo,

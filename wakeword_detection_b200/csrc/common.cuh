@@ -114,6 +114,7 @@ struct wwb_ctx {
   size_t ws_bytes[8] = {};
   int64_t launches = 0;
   void* debug_buf = nullptr;   // optional device buffer for kernel timeline dumps (wwb_debug_buffer)
+  void* host_pipe = nullptr;   // host-buffer pipeline state (host_pipeline.cu), created on first use
   std::string err;
   std::vector<void*> owned;    // device allocations to free
 };
@@ -123,6 +124,7 @@ namespace wwb {
 extern std::string g_create_error;
 
 int fail(wwb_ctx* ctx, int code, const char* fmt, ...);
+void host_pipe_destroy(wwb_ctx* ctx);
 
 #define WWB_CUDA(ctx, expr)                                                               \
   do {                                                                                    \
