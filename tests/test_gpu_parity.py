@@ -503,6 +503,34 @@ def test_wavenet_config4_stream_push_vs_oracle(wake_pcm, w_wavenet):
 
 
 
+def test_crnn_streaming_many_windows_per_push(w_crnn):
+    """4096 streams x 1600-sample chunks = up to 40960 windows per wwb_stream_push (beyond one 37888-window chunk of the
+    CRNN path): the push scores them all; two streams are checked against the oracle's trigger state machine, and a
+    capacity the library cannot serve is refused at wwb_stream_alloc, before any state exists."""
+    import torch
+    from wakeword_detection_b200 import _cabi
+    eng = _cabi.Engine(w_crnn, 0, "tc")
+    S = 4096
+    eng.stream_alloc(S, 1600)
+    assert eng.stream_max_frames() == 10
+    pcm = synth.device_pcm(S, 1600 * 4, seed=33, device=eng.device)
+    oracles = {sidx: R.TriggerOracle(w_crnn) for sidx in (0, 4095)}
+    for i in range(4):
+        post, npost, trig, pmax = eng.stream_push(pcm[:, i * 1600:(i + 1) * 1600].contiguous())
+        want = 7 if i == 0 else 10                     # (1600 - 512) // 160 + 1 = 7 frames complete in the first chunk
+        assert int(npost.min()) == want and int(npost.max()) == want
+        for sidx, o in oracles.items():
+            before = len(o.posteriors)
+            o(pcm[sidx, i * 1600:(i + 1) * 1600].cpu().numpy(), True)
+            ref = np.array(o.posteriors[before:], np.float32)
+            assert np.abs(post[sidx, :want].cpu().numpy() - ref).max() < POST_ATOL
+    eng.close()
+    big = _cabi.Engine(w_crnn, 0, "tc")
+    with pytest.raises(ValueError):
+        big.stream_alloc(200000, 1600)                 # 2 M windows per push: refused up front
+    big.close()
+
+
 # ------------------------------------------------------------------------------------ counters
 def test_eval_counts_vs_oracle(golden):
     eng = get_engine("CRNN")
@@ -772,6 +800,37 @@ def test_tf_lite_opts_models_predict_dropin(wname, name):
         ETO.models_predict(enc, det, X.astype(np.float64), wname)
     with pytest.raises(ValueError):
         ETO.models_predict(enc, det, X, "Wavenet" if wname == "CRNN" else "CRNN")
+
+
+@pytest.mark.parametrize("wname,name", [("CRNN", "crnn"), ("Wavenet", "wavenet")])
+def test_fp16_weight_variant_vs_oracle(wname, name):
+    """SURVEY 8(f) row 3 / utils/evaluate_tf_lite_opts.py:103-131: the float16-weight variant (constants rounded to
+    float16, float32 arithmetic) through the CUDA path against the oracle run on the SAME rounded weights (1e-3), plus the
+    accuracy report the reference's script is after: how far the variant's posteriors / decisions are from float32."""
+    import os
+    from conftest import WEIGHTS
+    from wakeword_detection_b200 import _cabi, weights as W, evaluate_tf_lite_opts as ETO
+    w = load_weights(wname)
+    wq = W.load_model_dir(os.path.join(WEIGHTS, wname), wname, quant=True)
+    X = _windows(name, w)
+    ref_q, ref_32 = R.posterior(X, wq), R.posterior(X, w)
+    eng = _cabi.engine_for_dir(os.path.join(WEIGHTS, wname), wname, quant=True)
+    post = eng.posteriors(X, hop=1).cpu().numpy()[:, 0]
+    assert np.abs(post - ref_q).max() < POST_ATOL
+    band = np.abs(ref_q - 0.5) <= POST_ATOL
+    assert np.array_equal((post > 0.5)[~band], (ref_q > 0.5)[~band])
+    drift = np.abs(ref_q - ref_32).max()
+    flips = int(((ref_q >= 0.5) != (ref_32 >= 0.5)).sum())
+    print("%s float16-weight variant: max |p16 - p32| = %.3e over %d windows, %d decision changes; CUDA vs oracle %.3e"
+          % (wname, drift, X.shape[0], flips, np.abs(post - ref_q).max()))
+    assert 1e-6 < drift < 5e-2                    # a different model (not the float32 one), but a close one
+    # the drop-in entry points: -quant files are not shipped, so the variant is derived on request only
+    enc, det = ETO.load_tf_models(os.path.join(WEIGHTS, wname), quant=True, derive_quant=True)
+    assert enc.quant and det.quant
+    p2 = ETO.posteriors(enc, det, X, wname)
+    np.testing.assert_array_equal(p2, post)
+    enc32, det32 = ETO.load_tf_models(os.path.join(WEIGHTS, wname))
+    assert np.abs(ETO.posteriors(enc32, det32, X, wname) - ref_32).max() < POST_ATOL      # the float32 pair is a different engine
 
 
 def test_dataset_filter_dropin(tmp_path, w_crnn):

@@ -218,3 +218,41 @@ def test_pcm_scaling_without_division_is_exact():
     assert np.all(rem.astype(np.float64) == s.astype(np.float64) - q0.astype(np.float64) * 32767.0)   # exact
     q = (rem.astype(np.float64) * np.float64(r) + q0.astype(np.float64)).astype(np.float32)
     assert np.array_equal(q, s / np.float32(32767.0))
+
+
+def test_fp16_weight_variant_loader_and_dequantize_folding():
+    """`*-quant.tflite` = trained constants stored as float16 behind DEQUANTIZE ops, float32 math
+    (wwdetect/CRNN/convert_CRNN_tflite.py:23-37).  The reader folds the op; without the files the variant is derived by the
+    converter's rounding; a missing `-quant` file raises like the interpreter unless derivation is asked for."""
+    import os
+    from conftest import WEIGHTS
+    from wakeword_detection_b200 import tflite_reader as tr, weights as W
+    from wakeword_detection_b200.models import TFLiteModel
+    # DEQUANTIZE folding on a hand-built graph: fp16 constant -> DEQUANTIZE -> FULLY_CONNECTED
+    w16 = np.array([[0.1, -2.5], [3.0, 1e-3]], np.float16)
+    tensors = [tr.Tensor(0, "in", [1, 2], np.float32, 0, None), tr.Tensor(1, "w16", [2, 2], np.float16, 1, w16),
+               tr.Tensor(2, "w32", [2, 2], np.float32, 0, None), tr.Tensor(3, "out", [1, 2], np.float32, 0, None)]
+    ops = [tr.Op(6, "DEQUANTIZE", [1], [2]), tr.Op(9, "FULLY_CONNECTED", [0, 2, -1], [3], {"act": 0})]
+    m = tr.fold_dequantize(tr.Model(3, "t", [tr.SubGraph("main", tensors, [0], [3], ops)]))
+    assert [o.name for o in m.main.ops] == ["FULLY_CONNECTED"]
+    assert m.main.tensors[2].data.dtype == np.float32 and np.array_equal(m.main.tensors[2].data, w16.astype(np.float32))
+    for name in ("CRNN", "Wavenet"):
+        d = os.path.join(WEIGHTS, name)
+        w = W.load_model_dir(d, name)
+        q = W.load_model_dir(d, name, quant=True)
+        assert str(q["quant_source"]) == "derived"
+        changed = 0
+        for k, v in w.items():
+            if k in ("mel_w", "mel_b", "mel_length", "dilation") or not isinstance(v, np.ndarray) or v.dtype != np.float32 or v.ndim == 0:
+                assert np.array_equal(q[k], v)                  # the filter and the geometry are untouched
+                continue
+            assert np.array_equal(q[k], q[k].astype(np.float16).astype(np.float32))   # exactly representable in fp16
+            assert np.abs(q[k] - v).max() <= 2.0 ** -11 * max(np.abs(v).max(), 6.2e-5) + 6e-8
+            changed += int((q[k] != v).any())
+        assert changed >= 8
+        q2 = W.quantize_fp16(q)
+        assert all(np.array_equal(q2[k], q[k]) for k in q if k != "quant_source")
+        with pytest.raises(ValueError):
+            TFLiteModel(os.path.join(d, "encode-quant.tflite"))   # not shipped: opening it fails like the interpreter
+    with pytest.raises(ValueError):
+        TFLiteModel(os.path.join(WEIGHTS, "CRNN", "filter-quant.tflite"), derive_quant=True)

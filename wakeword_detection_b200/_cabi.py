@@ -494,17 +494,18 @@ class Engine:
         self._check(self.lib.wwb_stream_reset(self.ctx, m.data_ptr() if m is not None else None, S, self._stream()))
 
 
-_ENGINES: Dict[Tuple[str, str, int], Engine] = {}
+_ENGINES: Dict[Tuple, Engine] = {}
 
 
-def engine_for_dir(model_dir: str, model_type: str, device: int = 0, precision: str = "tc") -> Engine:
-    """One shared Engine per (model directory, kind, device) — the reference builds three
-    interpreters per directory; here they share one context."""
+def engine_for_dir(model_dir: str, model_type: str, device: int = 0, precision: str = "tc", quant: bool = False) -> Engine:
+    """One shared Engine per (model directory, kind, device, precision, variant) — the reference builds three
+    interpreters per directory; here they share one context.  quant=True: the float16-weight variant
+    (weights.load_model_dir)."""
     from . import weights as W
 
-    key = (os.path.abspath(model_dir), W.model_kind(model_type), int(device))
+    key = (os.path.abspath(model_dir), W.model_kind(model_type), int(device), precision, bool(quant))
     eng = _ENGINES.get(key)
     if eng is None or eng.ctx is None:
-        eng = Engine(W.load_model_dir(model_dir, model_type), device=device, precision=precision)
+        eng = Engine(W.load_model_dir(model_dir, model_type, quant=quant), device=device, precision=precision)
         _ENGINES[key] = eng
     return eng

@@ -429,10 +429,29 @@ int wwb_eval_counts(wwb_ctx* ctx, const float* post, const int64_t* seg_off, int
                             (cudaStream_t)stream);
 }
 
+// the explicit window lists of a streaming push over the first S streams (filled by the plan kernel, filter.cu)
+static WinMap stream_map(const wwb_ctx* ctx, int64_t S) {
+  WinMap wm;
+  memset(&wm, 0, sizeof(wm));
+  wm.mel = ctx->st.mel_ring;
+  wm.win_stream = ctx->st.win_stream;
+  wm.win_start = ctx->st.win_start;
+  wm.n_win_dev = ctx->st.n_win;
+  wm.n_win = S * ctx->st.max_frames;
+  wm.n_streams = S;
+  wm.win_per_stream = 1;
+  wm.hop = 1;
+  wm.ring = ctx->st.ring;
+  return wm;
+}
+
 int wwb_stream_alloc(wwb_ctx* ctx, int64_t max_streams, int64_t max_chunk) {
   if (!ctx) return WWB_ERR_ARG;
   if (max_streams < 1 || max_chunk < 1 || max_chunk > 16000) return fail(ctx, WWB_ERR_ARG, "bad stream geometry");
   if (ctx->st.max_streams) return fail(ctx, WWB_ERR_STATE, "stream state already allocated");
+  if (max_streams * ((max_chunk - 1) / kHop + 1) > (1 << 20))
+    return fail(ctx, WWB_ERR_ARG, "%lld streams x %lld frames per push exceed 2^20 windows per push: split the streams over several contexts",
+                (long long)max_streams, (long long)((max_chunk - 1) / kHop + 1));
   WWB_CUDA(ctx, cudaSetDevice(ctx->device));
   StreamState& s = ctx->st;
   s.max_chunk = max_chunk;
@@ -455,6 +474,14 @@ int wwb_stream_alloc(wwb_ctx* ctx, int64_t max_streams, int64_t max_chunk) {
   if ((rc = dalloc(ctx, 1, &s.n_win))) return rc;
   if ((rc = dalloc(ctx, S * s.max_frames, &s.win_post))) return rc;
   s.max_streams = max_streams;
+  // Size the encoder's workspaces for the largest push now (a dry run over zero windows: n_win is 0 after dalloc), so that
+  // wwb_stream_push cannot fail on an allocation AFTER its filter stage has consumed the chunk and advanced the
+  // per-stream state.
+  if (ctx->kind != WWB_MODEL_NONE) {
+    WinMap wm = stream_map(ctx, max_streams);
+    if ((rc = run_posteriors(ctx, wm, nullptr, nullptr, s.win_post, 0))) { s.max_streams = 0; return rc; }
+    WWB_CUDA(ctx, cudaStreamSynchronize(0));
+  }
   return WWB_OK;
 }
 
@@ -470,19 +497,10 @@ int wwb_stream_push(wwb_ctx* ctx, const int16_t* pcm, int64_t S, int64_t n, cons
   if (!pcm) return fail(ctx, WWB_ERR_ARG, "NULL pcm");
   WWB_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->kind == WWB_MODEL_NONE) return fail(ctx, WWB_ERR_STATE, "ctx holds a filter only (no encode/detect weights)");
   int rc = launch_stream_filter(ctx, pcm, S, n, is_speech, is_active, a, st);
   if (rc) return rc;
-  WinMap wm;
-  memset(&wm, 0, sizeof(wm));
-  wm.mel = ctx->st.mel_ring;
-  wm.win_stream = ctx->st.win_stream;
-  wm.win_start = ctx->st.win_start;
-  wm.n_win_dev = ctx->st.n_win;
-  wm.n_win = S * ctx->st.max_frames;
-  wm.n_streams = S;
-  wm.win_per_stream = 1;
-  wm.hop = 1;
-  wm.ring = ctx->st.ring;
+  WinMap wm = stream_map(ctx, S);
   if ((rc = run_posteriors(ctx, wm, nullptr, nullptr, ctx->st.win_post, st))) return rc;
   return launch_stream_finish(ctx, S, is_speech, is_active, threshold, post_out, n_post_out, trigger_out,
                               post_max_out, st);

@@ -231,6 +231,9 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
   // (WWB_CRNN_NO_SHARE=1 forces the per-window path: used by the tests to check that both give identical bits)
   const char* no_share = getenv("WWB_CRNN_NO_SHARE");
   const bool shared = ctx->precision != WWB_PREC_F32 && !(no_share && no_share[0] == '1') && crnn_share_plan(wm, ctx->L, &sh);
+  // streaming pushes (device-side window count): one chunk - the kernels clamp to *n_win_dev, which chunks would have to
+  // offset; wwb_stream_alloc bounds streams x frames per push and sizes these workspaces up front
+  if (wm.n_win_dev) chunk = std::max<int64_t>(chunk, (B + 127) / 128 * 128);
   int64_t chunk_streams = 0;
   if (shared) {
     // intermediates are ~7.6 KB per window here (xwS 2.7 KB + packed layer-1 output 4.9 KB): chunks of up to 512 K windows
@@ -248,7 +251,6 @@ int crnn_simt_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float* 
   // layer-1 output: fp32 [B, 19, 64] (fp32 path) or the packed fp16 hi/lo operand of the fused layer-2 kernel (same bytes per value)
   if ((rc = workspace(ctx, 3, std::max((size_t)std::min(B, chunk) * C_T * 64 * 4, crnn_seq_packed_bytes(std::min(B, chunk))), &s1))) return rc;
   if ((rc = workspace(ctx, 4, (size_t)std::min(B, chunk) * 64 * 4, &enc_ws))) return rc;
-  if (wm.n_win_dev && B > chunk) return fail(ctx, WWB_ERR_ARG, "streaming batch too large");
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
     const int64_t nb = std::min(chunk, B - b0);
     WinMap sub = wm;

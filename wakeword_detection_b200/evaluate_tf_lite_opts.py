@@ -26,11 +26,13 @@ from .models import TFLiteModel
 _LABEL = "/is_hotword"
 
 
-def load_tf_models(models_dir, quant=False):
-    """evaluate_tf_lite_opts.py:16-33."""
+def load_tf_models(models_dir, quant=False, derive_quant=False):
+    """evaluate_tf_lite_opts.py:16-33.  quant=True opens `encode-quant.tflite` / `detect-quant.tflite` (weights stored as
+    float16, float32 arithmetic); with derive_quant=True a directory that only holds the float32 files gets the variant
+    derived by the converter's rounding instead of an error."""
     suffix = "-quant" if quant else ""
-    encode_model = TFLiteModel(model_path=os.path.join(models_dir, "encode%s.tflite" % suffix))
-    detect_model = TFLiteModel(model_path=os.path.join(models_dir, "detect%s.tflite" % suffix))
+    encode_model = TFLiteModel(model_path=os.path.join(models_dir, "encode%s.tflite" % suffix), derive_quant=derive_quant)
+    detect_model = TFLiteModel(model_path=os.path.join(models_dir, "detect%s.tflite" % suffix), derive_quant=derive_quant)
     return encode_model, detect_model
 
 
@@ -130,8 +132,7 @@ def parse_args(argv=None):
 
 
 def main(args) -> int:
-    """evaluate_tf_lite_opts.py:102-131.  The fp16-quantised pair is evaluated when its files exist
-    (SURVEY.md §8f row 3 - not shipped with the reference's model directories)."""
+    """evaluate_tf_lite_opts.py:102-131: float32 and float16-weight variants of the model directory."""
     start = time.time()
     encode_model, detect_model = load_tf_models(args.tf_models_dir)
     X, y = load_data(os.path.join(args.dataset_dir, args.testset), args.timesteps, args.num_features)
@@ -139,13 +140,13 @@ def main(args) -> int:
     print(f'Testing {args.model_type} TF-Lite models with 32-bit floats')
     preds = models_predict(encode_model, detect_model, X, args.model_type)
     results['float32'] = metrics(preds, y)
-    if os.path.isfile(os.path.join(args.tf_models_dir, "encode-quant.tflite")):
-        encode_q, detect_q = load_tf_models(args.tf_models_dir, quant=True)
-        print(f'Testing {args.model_type} TF-Lite models with 16-bit floats')
-        preds = models_predict(encode_q, detect_q, X, args.model_type)
-        results['float16'] = metrics(preds, y)
-    else:
-        print('no encode-quant.tflite in %s: float16 arm skipped' % args.tf_models_dir)
+    if not os.path.isfile(os.path.join(args.tf_models_dir, "encode-quant.tflite")):
+        print('no encode-quant.tflite in %s: the float16 arm runs on the float32 weights rounded to float16 '
+              '(what convert_*_tflite.py stores)' % args.tf_models_dir)
+    encode_q, detect_q = load_tf_models(args.tf_models_dir, quant=True, derive_quant=True)
+    print(f'Testing {args.model_type} TF-Lite models with 16-bit floats')
+    preds = models_predict(encode_q, detect_q, X, args.model_type)
+    results['float16'] = metrics(preds, y)
     pickle.dump(results, open(os.path.join(args.tf_models_dir, 'tf_lite_results.npy'), 'wb'))
     print(f'Script completed in {time.time()-start:.2f} secs')
     return 0

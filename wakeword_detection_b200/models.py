@@ -31,28 +31,37 @@ def _kind_of_dir(model_dir: str) -> str:
 
 
 class TFLiteModel:
-    """model_path: <dir>/filter.tflite | <dir>/encode.tflite | <dir>/detect.tflite.
-    `device` / `precision` are extensions (keyword only)."""
+    """model_path: <dir>/filter.tflite | <dir>/encode.tflite | <dir>/detect.tflite, or the float16 variants
+    <dir>/encode-quant.tflite | <dir>/detect-quant.tflite (reference: utils/evaluate_tf_lite_opts.py:16-33).  A
+    `-quant` file that does not exist raises like the interpreter would, unless `derive_quant=True`: then the variant is
+    derived from the float32 files by the converter's rounding (weights.quantize_fp16).
+    `device` / `precision` / `derive_quant` are extensions (keyword only)."""
 
     def __init__(self, model_path: str, **kwargs: Any) -> None:
         self.model_path = model_path
         model_dir = os.path.dirname(model_path) or "."
-        role = os.path.basename(model_path).split(".")[0].split("-")[0]
-        if role not in ("filter", "encode", "detect"):
-            raise ValueError("Could not open '%s': expected filter/encode/detect .tflite" % model_path)
-        have_file = os.path.isfile(model_path) or os.path.isfile(os.path.join(model_dir, "weights.npz"))
+        stem = os.path.basename(model_path).split(".")[0]
+        role, _, variant = stem.partition("-")
+        if role not in ("filter", "encode", "detect") or variant not in ("", "quant") or (role == "filter" and variant):
+            raise ValueError("Could not open '%s': expected filter/encode/detect[-quant] .tflite" % model_path)
+        quant = variant == "quant"
+        derive = bool(kwargs.pop("derive_quant", False))
+        have_file = os.path.isfile(model_path) or (not quant and os.path.isfile(os.path.join(model_dir, "weights.npz")))
+        if quant and not have_file and derive:
+            have_file = os.path.isfile(os.path.join(model_dir, role + ".tflite")) or os.path.isfile(os.path.join(model_dir, "weights.npz"))
         if not have_file:
             raise ValueError("Could not open '%s'." % model_path)
         self.role = role
+        self.quant = quant
         device = int(kwargs.pop("device", 0))
         precision = kwargs.pop("precision", "tc")
         kind = _kind_of_dir(model_dir)
         if role != "filter" and not kind:
             raise ValueError("Could not open '%s': no encode/detect weights in %s" % (model_path, model_dir))
         if kind:
-            self._engine = _cabi.engine_for_dir(model_dir, kind, device, precision)
+            self._engine = _cabi.engine_for_dir(model_dir, kind, device, precision, quant=quant)
         else:
-            key = (os.path.abspath(model_dir), "FILTER", device)
+            key = (os.path.abspath(model_dir), "FILTER", device, precision, False)
             eng = _cabi._ENGINES.get(key)
             if eng is None or eng.ctx is None:
                 eng = _cabi.Engine(W.extract_filter(os.path.join(model_dir, "filter.tflite")), device, precision)

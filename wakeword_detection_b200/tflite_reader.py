@@ -229,4 +229,23 @@ def load(path: str) -> Model:
                           _parse_options(fb, name, opt)))
         subgraphs.append(SubGraph(fb.string(sg, 4), tensors, fb.vec_i32(sg, 1),
                                   fb.vec_i32(sg, 2), ops))
-    return Model(fb.scalar(root, 0, "u32"), fb.string(root, 3), subgraphs)
+    return fold_dequantize(Model(fb.scalar(root, 0, "u32"), fb.string(root, 3), subgraphs))
+
+
+def fold_dequantize(model: Model) -> Model:
+    """fp16-quantised files (`encode-quant.tflite`, reference: wwdetect/CRNN/convert_CRNN_tflite.py:23-37,
+    wwdetect/wavenet/wavenet_model.py:149-163) store every trained constant as FLOAT16 behind a DEQUANTIZE op and
+    compute in float32.  Folding the op (output tensor := the constant widened to float32) leaves a graph of the same
+    shape as the float32 file, so the weight extractors and the literal interpreter read both alike."""
+    for g in model.subgraphs:
+        keep = []
+        for op in g.ops:
+            src = g.tensors[op.inputs[0]] if op.name == "DEQUANTIZE" and op.inputs else None
+            if src is not None and src.data is not None and src.data.dtype == np.float16:
+                dst = g.tensors[op.outputs[0]]
+                dst.data = src.data.astype(np.float32)
+                dst.dtype = np.float32
+                continue
+            keep.append(op)
+        g.ops = keep
+    return model

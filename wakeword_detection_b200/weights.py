@@ -296,9 +296,40 @@ def model_kind(model_type: str) -> str:
     return k
 
 
-def load_model_dir(model_dir: str, model_type: str) -> Dict[str, np.ndarray]:
-    """All trained tensors (filter + encode + detect) of a reference model directory."""
+# trained tensors of the encode / detect files (everything the converter's float16 option touches; filter.tflite is
+# never converted with it)
+_FILTER_KEYS = ("mel_w", "mel_b", "mel_floor", "mel_log_offset", "mel_scale")
+_NOT_TRAINED = ("mel_length", "dilation", "quant_source")
+
+
+def quantize_fp16(weights: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """The fp16-quantised variant of a model as the reference's converters produce it
+    (`optimizations=[DEFAULT]`, `supported_types=[float16]`: wwdetect/CRNN/convert_CRNN_tflite.py:23-37,
+    wwdetect/wavenet/wavenet_model.py:149-163): every trained float32 constant of encode / detect is stored as
+    float16 and widened back at run time, the arithmetic stays float32.  Idempotent."""
+    out = {}
+    for k, v in weights.items():
+        if k in _FILTER_KEYS or k in _NOT_TRAINED or not isinstance(v, np.ndarray) or v.dtype != np.float32:
+            out[k] = v
+        else:
+            out[k] = v.astype(np.float16).astype(np.float32)
+    out["quant_source"] = np.array("derived")
+    return out
+
+
+def load_model_dir(model_dir: str, model_type: str, quant: bool = False) -> Dict[str, np.ndarray]:
+    """All trained tensors (filter + encode + detect) of a reference model directory.
+    quant=True: the float16 variant - from `encode-quant.tflite` / `detect-quant.tflite` when the directory holds them
+    (`quant_source` = "file"), otherwise derived from the float32 files by the converter's rounding ("derived")."""
     kind = model_kind(model_type)
+    if quant:
+        enc, det = os.path.join(model_dir, "encode-quant.tflite"), os.path.join(model_dir, "detect-quant.tflite")
+        if os.path.isfile(enc) and os.path.isfile(det):
+            m = extract_crnn(enc, det) if kind == "CRNN" else extract_wavenet(enc, det)
+            m.update(extract_filter(os.path.join(model_dir, "filter.tflite")))
+            m["quant_source"] = np.array("file")
+            return m
+        return quantize_fp16(load_model_dir(model_dir, model_type))
     npz = os.path.join(model_dir, "weights.npz")
     if os.path.isfile(npz) and not os.path.isfile(os.path.join(model_dir, "encode.tflite")):
         with np.load(npz) as z:
