@@ -209,6 +209,27 @@ int wwb_stream_max_frames(const wwb_ctx* ctx);
 /* WakewordTrigger.reset (:241-246) for the streams whose mask byte is non-zero (NULL = all). */
 int wwb_stream_reset(wwb_ctx* ctx, const uint8_t* mask_dev, int64_t n_streams, void* stream);
 
+/* ---- the pipeline stages around the trigger, per stream on the device (SpeechPipeline._dispatch,
+ * spokestack/pipeline.py:25-28): VAD rise/fall debounce (spokestack/vad/webrtc.py:52-77; the raw
+ * per-frame decision of the webrtcvad C extension is an input) -> wake-word trigger (is_speech /
+ * is_active taken from this state; a trigger activates the stream) -> ActivationTimeout
+ * (spokestack/activation_timeout.py:25-38).  Needs wwb_stream_alloc first; delays in ms as the
+ * reference's constructors take them (rise/fall: integer division by frame_width; min/max_active:
+ * true division). */
+int wwb_context_alloc(wwb_ctx* ctx, int frame_width_ms, int vad_rise_delay_ms, int vad_fall_delay_ms,
+                      int min_active_ms, int max_active_ms);
+/* One dispatch for every stream: pcm_dev [n_streams, n] int16 (n = one pipeline frame, e.g. 320),
+ * vad_raw_dev uint8 [n_streams] (NULL = speech).  Outputs (device, any may be NULL): posteriors
+ * analysed in this call as in wwb_stream_push, and per stream context.is_speech / context.is_active
+ * after the three stages plus the activation / deactivation events of this call. */
+int wwb_context_step(wwb_ctx* ctx, const int16_t* pcm_dev, int64_t n_streams, int64_t n,
+                     const uint8_t* vad_raw_dev, float pre_emphasis, float threshold,
+                     float* post_out_dev, int32_t* n_post_out_dev, float* post_max_out_dev,
+                     uint8_t* is_speech_out_dev, uint8_t* is_active_out_dev,
+                     uint8_t* activated_out_dev, uint8_t* deactivated_out_dev, void* stream);
+/* all stages of all streams back to their initial state */
+int wwb_context_reset(wwb_ctx* ctx, void* stream);
+
 /* number of kernels this library has launched on ctx since creation (bench accounting) */
 int64_t wwb_launch_count(const wwb_ctx* ctx);
 /* development aid: device buffer (>= 8 KB, zeroed) that instrumented kernels fill with

@@ -326,3 +326,70 @@ class TriggerOracle:
                 self.pending = self.pending[HOP:]
         if vad_fall:
             self.reset()
+
+
+# ----------------------------------------------------------------------------
+# pipeline stages around the trigger
+class VadDebounceOracle:
+    """Rise / fall debounce of VoiceActivityDetector (spokestack/vad/webrtc.py:34-77); the raw per-frame decision of
+    the webrtcvad C extension is an input."""
+
+    def __init__(self, frame_width=20, vad_rise_delay=0, vad_fall_delay=0):
+        self.rise = vad_rise_delay // frame_width
+        self.fall = vad_fall_delay // frame_width
+        self.run_value, self.run_length = 0, 0
+
+    def __call__(self, is_speech: bool, raw: bool) -> bool:
+        raw = bool(raw)
+        if raw == self.run_value:
+            self.run_length += 1
+        else:
+            self.run_value, self.run_length = raw, 1
+        if self.run_value != is_speech:
+            if self.run_value and self.run_length >= self.rise:
+                is_speech = True
+            if not self.run_value and self.run_length >= self.fall:
+                is_speech = False
+        return is_speech
+
+
+class ActivationTimeoutOracle:
+    """spokestack/activation_timeout.py:16-38."""
+
+    def __init__(self, frame_width=20, min_active=500, max_active=5000):
+        self.min_active = min_active / frame_width
+        self.max_active = max_active / frame_width
+        self.is_speech, self.active_length = False, 0
+
+    def __call__(self, is_speech: bool, is_active: bool) -> bool:
+        vad_fall = self.is_speech and not is_speech
+        self.is_speech = is_speech
+        if is_active:
+            self.active_length += 1
+            if self.active_length > self.min_active:
+                if vad_fall or self.active_length > self.max_active:
+                    self.active_length = 0
+                    is_active = False
+        return is_active
+
+
+class PipelineOracle:
+    """One stream through vad -> wake-word trigger -> activation timeout, one call per frame
+    (SpeechPipeline._dispatch, spokestack/pipeline.py:25-28)."""
+
+    def __init__(self, w, threshold=0.5, a=0.0, frame_width=20, vad_rise_delay=0, vad_fall_delay=0, min_active=500,
+                 max_active=5000):
+        self.vad = VadDebounceOracle(frame_width, vad_rise_delay, vad_fall_delay)
+        self.trig = TriggerOracle(w, threshold, a)
+        self.tmo = ActivationTimeoutOracle(frame_width, min_active, max_active)
+        self.is_speech = False
+
+    @property
+    def is_active(self):
+        return self.trig.active
+
+    def __call__(self, frame: np.ndarray, raw_vad: bool):
+        self.is_speech = self.vad(self.is_speech, raw_vad)
+        self.trig(frame, self.is_speech)
+        self.trig.active = self.tmo(self.is_speech, self.trig.active)
+        return self.is_speech, self.trig.active

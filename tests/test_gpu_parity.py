@@ -652,6 +652,51 @@ def test_multistream_trigger_vs_oracle(wake_pcm, w_crnn):
     ms.close()
 
 
+@pytest.mark.parametrize("wname,name", [("CRNN", "crnn"), ("Wavenet", "wavenet")])
+def test_device_pipeline_state_machine_replays_reference_run(wname, name):
+    """vad debounce -> trigger -> activation timeout for many streams on the device
+    (wwb_context_step) against (a) the golden run of the reference's own three stages (stream 0) and (b) the oracle's
+    PipelineOracle on streams with other raw-VAD scripts / audio (time-shifted copies)."""
+    import os
+    from conftest import GOLDEN, WEIGHTS
+    from wakeword_detection_b200.wakeword import MultiStreamPipeline
+    w = load_weights(wname)
+    g = np.load(os.path.join(GOLDEN, "reference_pipeline.npz"))
+    cfg = dict(zip(("frame_width", "vad_rise_delay", "vad_fall_delay", "min_active", "max_active"), [int(v) for v in g["cfg"]]))
+    pcm0, raw0 = g["pipe_%s_pcm" % name], g["pipe_%s_raw" % name]
+    nf = len(raw0)
+    S = 5
+    rng = np.random.default_rng(11)
+    pcm = np.stack([np.roll(pcm0, 320 * 7 * s) for s in range(S)])
+    raw = np.stack([raw0] + [np.roll(raw0, 7 * s) ^ (rng.random(nf) < 0.03) for s in range(1, S)])
+    raw[4] = True                                        # a stream whose VAD never falls: only max_active ends activations
+    pipe = MultiStreamPipeline(os.path.join(WEIGHTS, wname), wname, S, **cfg)
+    oracles = [R.PipelineOracle(w, **cfg) for _ in range(S)]
+    acts = np.zeros((nf, S), bool)
+    for i in range(nf):
+        out = pipe.step(pcm[:, i * 320:(i + 1) * 320], raw[:, i])
+        sp, ac = out["is_speech"].cpu().numpy().astype(bool), out["is_active"].cpu().numpy().astype(bool)
+        acts[i] = ac
+        for s in range(S):
+            o = oracles[s]
+            before = len(o.trig.posteriors)
+            want_sp, want_ac = o(pcm[s, i * 320:(i + 1) * 320], raw[s, i])
+            new = np.array(o.trig.posteriors[before:], np.float32)
+            near = new.size and np.abs(new - 0.5).min() <= POST_ATOL
+            assert sp[s] == want_sp, (i, s)
+            assert int(out["n_post"][s]) == new.size, (i, s)
+            if new.size:
+                assert np.abs(out["post"][s, :new.size].cpu().numpy() - new).max() < POST_ATOL
+            if not near:
+                assert ac[s] == want_ac, (i, s)
+    np.testing.assert_array_equal(acts[:, 0], g["pipe_%s_active" % name])      # the reference's own run
+    assert acts[:, 0].any() and not acts[-1, 0] or name == "crnn"
+    pipe.reset()
+    out = pipe.step(pcm[:, :320], raw[:, 0])
+    assert not out["is_active"].any()
+    pipe.close()
+
+
 def test_tflite_model_and_filter_dropins(golden, w_crnn):
     import os
     from conftest import WEIGHTS

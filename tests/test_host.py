@@ -256,3 +256,50 @@ def test_fp16_weight_variant_loader_and_dequantize_folding():
             TFLiteModel(os.path.join(d, "encode-quant.tflite"))   # not shipped: opening it fails like the interpreter
     with pytest.raises(ValueError):
         TFLiteModel(os.path.join(WEIGHTS, "CRNN", "filter-quant.tflite"), derive_quant=True)
+
+
+def load_weights_host(name):
+    from conftest import load_weights
+    return load_weights(name)
+
+
+def test_vad_debounce_and_activation_timeout_dropins_replay_reference_run():
+    """tests/golden/reference_pipeline.npz = the reference's own VoiceActivityDetector / WakewordTrigger /
+    ActivationTimeout dispatched frame by frame (make_golden_pipeline.py).  The host drop-ins reproduce the VAD debounce
+    from the scripted raw decisions and, given the trigger's activations, the timeout's deactivations; so does the
+    oracle's PipelineOracle end to end (CRNN run, CPU)."""
+    import os
+    from conftest import GOLDEN
+    from oracle import restated as R
+    from wakeword_detection_b200.activation_timeout import ActivationTimeout
+    from wakeword_detection_b200.context import SpeechContext
+    from wakeword_detection_b200.vad import VoiceActivityDetector, VoiceActivityTrigger
+    g = np.load(os.path.join(GOLDEN, "reference_pipeline.npz"))
+    cfg = dict(zip(("frame_width", "vad_rise_delay", "vad_fall_delay", "min_active", "max_active"), [int(v) for v in g["cfg"]]))
+    for name in ("crnn", "wavenet"):
+        raw, speech, active = g["pipe_%s_raw" % name], g["pipe_%s_speech" % name], g["pipe_%s_active" % name]
+        it = iter(raw)
+        vad = VoiceActivityDetector(detector=lambda b, sr: bool(next(it)), **cfg)
+        tmo = ActivationTimeout(**cfg)
+        ctx = SpeechContext()
+        prev = False
+        for i in range(len(raw)):
+            vad(ctx, np.zeros(320, np.int16))
+            assert ctx.is_speech == bool(speech[i]), (name, i)
+            # the trigger's part: an activation shows up as a rising edge that the timeout did not cause
+            if active[i] and not prev:
+                ctx.is_active = True
+            tmo(ctx)
+            assert ctx.is_active == bool(active[i]), (name, i)
+            prev = bool(active[i])
+    vt, ctx = VoiceActivityTrigger(), SpeechContext()
+    ctx.is_speech = True
+    vt(ctx)
+    assert ctx.is_active
+    with pytest.raises(ImportError):
+        VoiceActivityDetector()            # webrtcvad is not installed here: the decision function must be injected
+    w = load_weights_host("CRNN")
+    o = R.PipelineOracle(w, **cfg)
+    pcm, raw = g["pipe_crnn_pcm"], g["pipe_crnn_raw"]
+    got = [o(pcm[i * 320:(i + 1) * 320], raw[i]) for i in range(len(raw))]
+    assert [s for s, _ in got] == list(g["pipe_crnn_speech"]) and [a for _, a in got] == list(g["pipe_crnn_active"])

@@ -68,6 +68,9 @@ PROTOTYPES = {
     "wwb_stream_push": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp]),
     "wwb_stream_max_frames": (C.c_int, [_vp]),
     "wwb_stream_reset": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "wwb_context_alloc": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "wwb_context_step": (C.c_int, [_vp, _vp, _i64, _i64, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wwb_context_reset": (C.c_int, [_vp, _vp]),
     "wwb_launch_count": (_i64, [_vp]),
     "wwb_debug_buffer": (C.c_int, [_vp, _vp]),
 }
@@ -481,6 +484,39 @@ class Engine:
             ac.data_ptr() if ac is not None else None, float(pre_emphasis), float(threshold),
             post.data_ptr(), npost.data_ptr(), trig.data_ptr(), pmax.data_ptr(), self._stream()))
         return post, npost, trig, pmax
+
+    def context_alloc(self, frame_width: int = 20, vad_rise_delay: int = 0, vad_fall_delay: int = 0, min_active: int = 500,
+                      max_active: int = 5000) -> None:
+        """Per-stream VAD debounce + ActivationTimeout state next to the streaming trigger (wwb_context_alloc)."""
+        self._check(self.lib.wwb_context_alloc(self.ctx, int(frame_width), int(vad_rise_delay), int(vad_fall_delay),
+                                               int(min_active), int(max_active)))
+
+    def context_step(self, pcm, vad_raw=None, pre_emphasis: float = 0.0, threshold: float = 0.5):
+        """One SpeechPipeline dispatch for every stream: vad debounce -> wake-word trigger -> activation timeout.
+        pcm [S, n] int16, vad_raw [S] (None = speech) -> dict of device tensors: post [S, max_frames] (NaN = none),
+        n_post, post_max, is_speech, is_active, activated, deactivated."""
+        t = self.torch
+        x = self._dev(pcm, t.int16)
+        if x.dim() == 1:
+            x = x[None]
+        S, n = x.shape
+        mf = self.stream_max_frames()
+        raw = None
+        if vad_raw is not None:
+            raw = vad_raw.to(self.device, t.uint8) if isinstance(vad_raw, t.Tensor) else self._dev(np.asarray(vad_raw), t.uint8)
+        out = {"post": t.empty((S, mf), dtype=t.float32, device=self.device),
+               "n_post": t.empty((S,), dtype=t.int32, device=self.device),
+               "post_max": t.empty((S,), dtype=t.float32, device=self.device)}
+        for k in ("is_speech", "is_active", "activated", "deactivated"):
+            out[k] = t.empty((S,), dtype=t.uint8, device=self.device)
+        self._check(self.lib.wwb_context_step(
+            self.ctx, x.data_ptr(), S, n, raw.data_ptr() if raw is not None else None, float(pre_emphasis), float(threshold),
+            out["post"].data_ptr(), out["n_post"].data_ptr(), out["post_max"].data_ptr(), out["is_speech"].data_ptr(),
+            out["is_active"].data_ptr(), out["activated"].data_ptr(), out["deactivated"].data_ptr(), self._stream()))
+        return out
+
+    def context_reset(self) -> None:
+        self._check(self.lib.wwb_context_reset(self.ctx, self._stream()))
 
     def stream_reset(self, mask=None) -> None:
         t = self.torch

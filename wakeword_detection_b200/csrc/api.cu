@@ -514,6 +514,63 @@ int wwb_stream_reset(wwb_ctx* ctx, const uint8_t* mask, int64_t S, void* stream)
   return launch_stream_reset(ctx, mask, S, (cudaStream_t)stream);
 }
 
+int wwb_context_alloc(wwb_ctx* ctx, int frame_width_ms, int vad_rise_delay_ms, int vad_fall_delay_ms, int min_active_ms,
+                      int max_active_ms) {
+  if (!ctx) return WWB_ERR_ARG;
+  if (!ctx->st.max_streams) return fail(ctx, WWB_ERR_STATE, "wwb_stream_alloc has not been called");
+  if (ctx->cs.max_streams) return fail(ctx, WWB_ERR_STATE, "context state already allocated");
+  if (frame_width_ms < 1 || vad_rise_delay_ms < 0 || vad_fall_delay_ms < 0 || min_active_ms < 0 || max_active_ms < 0)
+    return fail(ctx, WWB_ERR_ARG, "bad pipeline timing");
+  WWB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ContextState& c = ctx->cs;
+  const size_t S = (size_t)ctx->st.max_streams;
+  c.rise_length = vad_rise_delay_ms / frame_width_ms;          // vad/webrtc.py:43-44 (integer division)
+  c.fall_length = vad_fall_delay_ms / frame_width_ms;
+  c.min_active = (float)min_active_ms / (float)frame_width_ms; // activation_timeout.py:20-21 (true division)
+  c.max_active = (float)max_active_ms / (float)frame_width_ms;
+  int rc;
+  if ((rc = dalloc(ctx, S, &c.run_value))) return rc;
+  if ((rc = dalloc(ctx, S, &c.run_length))) return rc;
+  if ((rc = dalloc(ctx, S, &c.is_speech))) return rc;
+  if ((rc = dalloc(ctx, S, &c.is_active))) return rc;
+  if ((rc = dalloc(ctx, S, &c.active_length))) return rc;
+  if ((rc = dalloc(ctx, S, &c.t_is_speech))) return rc;
+  if ((rc = dalloc(ctx, S, &c.trigger))) return rc;
+  c.max_streams = (int64_t)S;
+  return WWB_OK;
+}
+
+int wwb_context_step(wwb_ctx* ctx, const int16_t* pcm, int64_t S, int64_t n, const uint8_t* vad_raw, float a, float threshold,
+                     float* post_out, int32_t* n_post_out, float* post_max_out, uint8_t* is_speech_out, uint8_t* is_active_out,
+                     uint8_t* activated_out, uint8_t* deactivated_out, void* stream) {
+  if (!ctx) return WWB_ERR_ARG;
+  if (!ctx->cs.max_streams) return fail(ctx, WWB_ERR_STATE, "wwb_context_alloc has not been called");
+  if (S < 1 || S > ctx->cs.max_streams) return fail(ctx, WWB_ERR_STATE, "n_streams %lld exceeds capacity %lld", (long long)S, (long long)ctx->cs.max_streams);
+  WWB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_context_vad(ctx, vad_raw, S, st);
+  if (rc) return rc;
+  if ((rc = wwb_stream_push(ctx, pcm, S, n, ctx->cs.is_speech, ctx->cs.is_active, a, threshold, post_out, n_post_out,
+                            ctx->cs.trigger, post_max_out, stream))) return rc;
+  return launch_context_timeout(ctx, ctx->cs.trigger, S, is_speech_out, is_active_out, activated_out, deactivated_out, st);
+}
+
+int wwb_context_reset(wwb_ctx* ctx, void* stream) {
+  if (!ctx) return WWB_ERR_ARG;
+  if (!ctx->cs.max_streams) return fail(ctx, WWB_ERR_STATE, "wwb_context_alloc has not been called");
+  WWB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  ContextState& c = ctx->cs;
+  const size_t S = (size_t)c.max_streams;
+  WWB_CUDA(ctx, cudaMemsetAsync(c.run_value, 0, S * 4, st));
+  WWB_CUDA(ctx, cudaMemsetAsync(c.run_length, 0, S * 4, st));
+  WWB_CUDA(ctx, cudaMemsetAsync(c.is_speech, 0, S, st));
+  WWB_CUDA(ctx, cudaMemsetAsync(c.is_active, 0, S, st));
+  WWB_CUDA(ctx, cudaMemsetAsync(c.active_length, 0, S * 4, st));
+  WWB_CUDA(ctx, cudaMemsetAsync(c.t_is_speech, 0, S, st));
+  return wwb_stream_reset(ctx, nullptr, c.max_streams, stream);
+}
+
 int64_t wwb_launch_count(const wwb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int wwb_debug_buffer(wwb_ctx* ctx, void* dev_buf) {

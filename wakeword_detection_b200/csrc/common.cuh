@@ -92,6 +92,20 @@ struct StreamState {
   float* win_post = nullptr;    // [S*max_frames]
 };
 
+// per-stream state of the pipeline stages around the trigger (context.cu)
+struct ContextState {
+  int64_t max_streams = 0;
+  int rise_length = 0, fall_length = 0;   // vad_rise_delay // frame_width, vad_fall_delay // frame_width (frames)
+  float min_active = 0.f, max_active = 0.f;   // min_active / frame_width, max_active / frame_width (frames, fractional)
+  int32_t* run_value = nullptr;   // [S] VoiceActivityDetector._run_value
+  int32_t* run_length = nullptr;  // [S]
+  uint8_t* is_speech = nullptr;   // [S] SpeechContext.is_speech
+  uint8_t* is_active = nullptr;   // [S] SpeechContext.is_active
+  int32_t* active_length = nullptr;  // [S] ActivationTimeout._active_length
+  uint8_t* t_is_speech = nullptr;    // [S] ActivationTimeout._is_speech
+  uint8_t* trigger = nullptr;        // [S] scratch: the push's trigger output
+};
+
 }  // namespace wwb
 
 struct wwb_ctx {
@@ -109,6 +123,7 @@ struct wwb_ctx {
   wwb::CrnnWeights crnn;
   wwb::WavenetWeights wn;
   wwb::StreamState st;
+  wwb::ContextState cs;
   // growable workspaces
   void* ws[8] = {};
   size_t ws_bytes[8] = {};
@@ -157,6 +172,9 @@ int launch_stream_finish(wwb_ctx* ctx, int64_t S, const uint8_t* is_speech, cons
                          float threshold, float* post_out, int32_t* n_post_out, uint8_t* trigger_out,
                          float* post_max_out, cudaStream_t st);
 int launch_stream_reset(wwb_ctx* ctx, const uint8_t* mask, int64_t S, cudaStream_t st);
+int launch_context_vad(wwb_ctx* ctx, const uint8_t* vad_raw, int64_t S, cudaStream_t st);
+int launch_context_timeout(wwb_ctx* ctx, const uint8_t* trigger, int64_t S, uint8_t* is_speech_out, uint8_t* is_active_out,
+                           uint8_t* activated_out, uint8_t* deactivated_out, cudaStream_t st);
 
 // window addressing shared by the encoders: window b reads rows
 //   mel + (stream(b)*ring + (start(b)+t) % ring) * 40,  t = 0..L-1

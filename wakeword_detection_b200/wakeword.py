@@ -50,6 +50,38 @@ class MultiStreamTrigger:
         self.engine.close()
 
 
+class MultiStreamPipeline:
+    """S independent speech pipelines [vad debounce -> WakewordTrigger -> ActivationTimeout] advanced by one call, all
+    state on the device (reference: spokestack/pipeline.py:25-28 dispatching spokestack/vad/webrtc.py:52-77,
+    spokestack/wakeword/tflite.py:123-246, spokestack/activation_timeout.py:25-38).  The raw per-frame VAD decision is an
+    input (the webrtcvad C extension is outside the path).
+
+    step(pcm[S, n] int16, vad_raw[S]) -> dict of device tensors: post, n_post, post_max, is_speech, is_active,
+    activated, deactivated."""
+
+    def __init__(self, model_dir: str, model_type: str, n_streams: int, frame_width: int = 20, sample_rate: int = 16000,
+                 pre_emphasis: float = 0.0, posterior_threshold: float = 0.5, vad_rise_delay: int = 0,
+                 vad_fall_delay: int = 0, min_active: int = 500, max_active: int = 5000, device: int = 0,
+                 precision: str = "tc") -> None:
+        from . import weights as W
+        self.engine = _cabi.Engine(W.load_model_dir(model_dir, model_type), device, precision)
+        self.n_streams = int(n_streams)
+        self.frame_samples = int(frame_width * sample_rate / 1000)
+        self.pre_emphasis = float(pre_emphasis)
+        self.threshold = float(posterior_threshold)
+        self.engine.stream_alloc(self.n_streams, self.frame_samples)
+        self.engine.context_alloc(frame_width, vad_rise_delay, vad_fall_delay, min_active, max_active)
+
+    def step(self, pcm, vad_raw=None):
+        return self.engine.context_step(pcm, vad_raw, self.pre_emphasis, self.threshold)
+
+    def reset(self) -> None:
+        self.engine.context_reset()
+
+    def close(self) -> None:
+        self.engine.close()
+
+
 class WakewordTrigger:
     """Detects the presence of a wakeword in the audio input (single stream)."""
 
@@ -64,8 +96,8 @@ class WakewordTrigger:
         device = int(kwargs.pop("device", 0))
         precision = kwargs.pop("precision", "tc")
         max_chunk = int(kwargs.pop("max_chunk_samples", 1600))
-        self._multi = MultiStreamTrigger(model_dir, model_type, 1, max_chunk, pre_emphasis,
-                                         posterior_threshold, device, precision)
+        self._multi_args = (model_dir, model_type, 1, max_chunk, pre_emphasis, posterior_threshold, device, precision)
+        self._multi = MultiStreamTrigger(*self._multi_args)
         e = self._multi.engine
         self._window_size = (e.n_bins - 1) * 2
         if self.hop_length != 160:
@@ -109,6 +141,8 @@ class WakewordTrigger:
         self._is_speech = context.is_speech
         was_active = bool(context.is_active)
         frame = np.ascontiguousarray(frame, dtype=np.int16)
+        if self._multi is None:      # the stage is used again after close(): a fresh device context, like a fresh interpreter
+            self._multi = MultiStreamTrigger(*self._multi_args)
         out = self._multi.push(frame[None, :], np.array([context.is_speech], np.uint8),
                                np.array([was_active], np.uint8))
         n = int(out["n_post"][0])
@@ -134,11 +168,16 @@ class WakewordTrigger:
             pass
 
     def reset(self) -> None:
-        self._multi.reset()
+        if self._multi is not None:
+            self._multi.reset()
         self.sample_window.reset()
         self.frame_window.reset().fill(0.0)
         self.encode_window.reset().fill(-1.0)
         self._posterior_max = 0.0
 
     def close(self) -> None:
+        """:248-250 resets the stage; here it also releases the device context (weights, stream state, workspaces)."""
         self.reset()
+        if self._multi is not None:
+            self._multi.close()
+            self._multi = None
