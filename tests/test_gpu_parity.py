@@ -763,6 +763,37 @@ def test_get_posterior_and_sweep_dropin(wname, name, golden):
     np.testing.assert_array_equal(FAR, golden["sweep_%s_far" % name])
 
 
+@pytest.mark.parametrize("wname", ["CRNN_arik_original", "Wavenet"])
+def test_sharded_evaluation_sums_to_single_process(wname, wake_pcm):
+    """utils/evaluate_models.py:280-327 sharded over 1 / 2 / 4 / 8 (virtual) ranks on the CUDA path: contiguous runs of
+    wake-word clips with the carried window + time chunks of the long false-accept clip with the (L-1)*160+352-sample
+    PCM halo; the per-rank counters add up EXACTLY to the single-process sweep (the all-reduce itself is covered by
+    the gloo world-2 test on CPU and by bench.py under torchrun)."""
+    import os
+    from conftest import WEIGHTS
+    from wakeword_detection_b200 import evaluate_models as EM, _cabi
+    typ = "Wavenet" if wname == "Wavenet" else "CRNN"
+    d = os.path.join(WEIGHTS, wname)
+    eng = _cabi.engine_for_dir(d, typ)
+    wake = wake_pcm["wavenet" if typ == "Wavenet" else "crnn"].astype(np.float32) / 32768.0
+    noise = lambda n, c, k: np.clip(synth.stream_float(n, c, 9, k), -1, 1).astype(np.float32)
+    pos = [wake, noise(20321, 2, 1), wake[3000:30000], noise(16777, 0, 2), wake[:33001], noise(30000, 5, 3), wake[100:]]
+    far = np.concatenate([noise(140000, 5, 4), wake, noise(252345, 2, 5), wake[:30000], noise(99999, 0, 6)])
+    thr = R.thresholds_eval()
+    kp = EM.get_posterior(d, typ, "false_negatives", pos, 20, 16000, engine=eng)
+    nk = EM.get_posterior(d, typ, "false_accepts", [far], 20, 16000, engine=eng)
+    acc1, edg1 = EM.sweep_counts(kp, nk, thr, eng)
+    assert acc1[0] >= 2 and edg1[0] >= 1
+    for world in (1, 2, 4, 8):
+        acc, edg = np.zeros_like(acc1), np.zeros_like(edg1)
+        for r in range(world):
+            a, e = EM.evaluate_sharded(d, typ, pos, far, 20, 16000, thr, rank=r, world=world, engine=eng, reduce_over_ranks=False)
+            acc += a
+            edg += e
+        np.testing.assert_array_equal(acc, acc1)
+        np.testing.assert_array_equal(edg, edg1)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("wname", ["CRNN", "Wavenet"])
 def test_encoders_are_deterministic(wname):

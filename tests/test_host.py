@@ -303,3 +303,132 @@ def test_vad_debounce_and_activation_timeout_dropins_replay_reference_run():
     pcm, raw = g["pipe_crnn_pcm"], g["pipe_crnn_raw"]
     got = [o(pcm[i * 320:(i + 1) * 320], raw[i]) for i in range(len(raw))]
     assert [s for s, _ in got] == list(g["pipe_crnn_speech"]) and [a for _, a in got] == list(g["pipe_crnn_active"])
+
+
+class _OracleEngine:
+    """CPU stand-in for `_cabi.Engine` in the host-logic tests of the sharded evaluation: same methods, answers from the
+    oracle (tests may use oracle/; the product path never does)."""
+
+    def __init__(self, w):
+        import torch
+        from oracle import restated as R
+        self.w, self.R, self.torch = w, R, torch
+        self.device = torch.device("cpu")
+        self.L = int(w["mel_length"])
+
+    def num_frames(self, n):
+        return 0 if n < 512 else (n - 512) // 160 + 1
+
+    def num_windows(self, f, hop):
+        return 0 if f < self.L else (f - self.L) // hop + 1
+
+    def pipeline(self, pcm, hop=2, pre_emphasis=0.0):
+        R = self.R
+        x = pcm.numpy()
+        nw = self.num_windows(self.num_frames(x.shape[1]), hop)
+        out = np.zeros((x.shape[0], nw), np.float32)
+        for i in range(x.shape[0]):
+            mel = R.mel_stream(x[i], self.w)
+            if nw:
+                j = np.arange(nw)
+                out[i] = R.posterior(mel[(hop * j)[:, None] + np.arange(self.L)[None, :]], self.w)
+        return self.torch.from_numpy(out)
+
+    def eval_counts(self, post, seg_off, thresholds, mode, smooth=30, halo_lo=None, halo_hi=None):
+        R = self.R
+        p = np.asarray(post, np.float32).reshape(-1)
+        seg = np.asarray(seg_off)
+        counts = np.zeros(len(thresholds), np.int64)
+        for k in range(len(seg) - 1):
+            part = p[seg[k]:seg[k + 1]]
+            if mode == "frr_max":
+                counts += np.array([int(part.max() > t) for t in thresholds])
+            else:
+                lo = halo_lo[k] if halo_lo is not None else 0
+                hi = halo_hi[k] if halo_hi is not None else 0
+                sm = R.smooth_same(part)
+                for ti, t in enumerate(thresholds):
+                    above = sm > t
+                    idx = np.arange(lo, part.size - hi)
+                    prev = np.where(idx > 0, above[np.maximum(idx - 1, 0)], False)
+                    counts[ti] += int((above[idx] & ~prev).sum())
+        return self.torch.from_numpy(counts)
+
+
+def _sharded_eval_inputs():
+    from conftest import GOLDEN
+    from wakeword_detection_b200 import synth
+    wake = np.load(os.path.join(GOLDEN, "wake_crnn_pcm.npy")).astype(np.float32) / 32768.0
+    pos = [wake, np.clip(synth.stream_float(20321, 2, 9, 1), -1, 1).astype(np.float32), wake[3000:30000],
+           np.clip(synth.stream_float(16777, 0, 9, 2), -1, 1).astype(np.float32), wake[:33001]]
+    far = np.concatenate([np.clip(synth.stream_float(40000, 5, 9, 3), -1, 1).astype(np.float32), wake,
+                          np.clip(synth.stream_float(52345, 2, 9, 4), -1, 1).astype(np.float32), wake[:30000]])
+    return pos, far
+
+
+def _sharded_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pos, far = _sharded_eval_inputs()
+    eng = _OracleEngine(load_weights_host("CRNN"))
+    thr = np.arange(0.5, 0.99999, 0.05)
+    acc, edg = EM.evaluate_sharded("", "CRNN", pos, far, 20, 16000, thr, engine=eng)
+    out.put((rank, acc.tolist(), edg.tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharded_evaluation_gloo_world2_equals_single_process():
+    """utils/evaluate_models.py:280-327 over two ranks (gloo on CPU, posteriors from the oracle): wake-word clips in
+    contiguous runs with the carried window, the long false-accept clip in two time chunks with PCM + counter halos,
+    ONE all-reduce - the counters equal the single-process sweep on every rank.  Also the pure partition rules."""
+    import torch.multiprocessing as mp
+    pos, far = _sharded_eval_inputs()
+    eng = _OracleEngine(load_weights_host("CRNN"))
+    thr = np.arange(0.5, 0.99999, 0.05)
+    kp = EM.get_posterior("", "CRNN", "false_negatives", pos, 20, 16000, engine=eng)
+    nk = EM.get_posterior("", "CRNN", "false_accepts", [far], 20, 16000, engine=eng)
+    acc1, edg1 = EM.sweep_counts(kp, nk, thr, eng)
+    assert acc1[0] >= 3 and edg1[0] >= 2                  # the wake clips fire in both sets
+    # a rank's run of clips, started with the carried window, gives the same maxima as the whole list
+    carries = EM.carry_before_clips([len(c) for c in pos], 16000, 320)
+    assert carries[0] == 0 and carries[1] == 480
+    tail = EM.get_posterior("", "CRNN", "false_negatives", pos[2:], 20, 16000, engine=eng, carry_len=carries[2])
+    np.testing.assert_array_equal(np.array(tail, np.float32), np.array(kp[2:], np.float32))
+    # time chunks of the FAR clip: the chunk's posteriors are the global trajectory's, for any world size
+    for world in (2, 3):
+        got = []
+        for r in range(world):
+            part, lo, hi, n_win = EM.far_chunk_posteriors(far, 20, 16000, r, world, eng)
+            assert n_win == len(nk)
+            got.append(part[lo:part.size - hi])
+            b, e, _, _ = wdist.time_chunks(n_win, world)[r]
+            np.testing.assert_allclose(part, np.array(nk[b - lo:e + hi], np.float32), atol=2e-6)
+        assert sum(g.size for g in got) == len(nk)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 7) % 1000
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for _, acc, edg in res:
+        assert acc == acc1.tolist() and edg == edg1.tolist()
+
+
+def test_load_wav_range(tmp_path):
+    pcm = (np.random.default_rng(3).standard_normal(5000) * 3000).astype(np.int16)
+    EM.concatenate_FA([pcm], 1, tmp_path / "y.wav")
+    whole = EM.load_wav(tmp_path / "y.wav", 16000)
+    assert EM.clip_num_samples(tmp_path / "y.wav", 16000) == 5000 and EM.clip_num_samples(whole, 16000) == 5000
+    for a, b in ((0, 5000), (-100, 300), (4900, 5200), (1234, 2345), (6000, 6100)):
+        want = np.zeros(b - a, np.float32)
+        lo, hi = max(a, 0), min(b, 5000)
+        if hi > lo:
+            want[lo - a:hi - a] = whole[lo:hi]
+        np.testing.assert_array_equal(EM.load_wav_range(tmp_path / "y.wav", a, b, 16000), want)
+        np.testing.assert_array_equal(EM.load_wav_range(whole, a, b, 16000), want)
