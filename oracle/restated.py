@@ -393,3 +393,43 @@ class PipelineOracle:
         self.trig(frame, self.is_speech)
         self.trig.active = self.tmo(self.is_speech, self.trig.active)
         return self.is_speech, self.trig.active
+
+
+class KeywordOracle:
+    """spokestack/asr/keyword/tflite.py:15-191 for one stream, with the encoder / detector as callables (the reference
+    ships no keyword model): returns the list of (kind, class index, confidence) events a frame produced."""
+
+    def __init__(self, w, encode_model, detect_model, threshold=0.5, a=0.97):
+        self.w, self.enc, self.det, self.thr, self.a = w, encode_model, detect_model, threshold, a
+        self.L = int(encode_model.input_details[0]["shape"][1])
+        self.EL, self.EW = (int(v) for v in detect_model.input_details[0]["shape"][1:])
+        self.state = np.zeros(encode_model.input_details[1]["shape"], F32)
+        self.prev_sample, self.was_active = 0.0, False
+        self.reset()
+
+    def reset(self):
+        self.pending = np.zeros((0,), F32)
+        self.frames = np.zeros((self.L, self.w["mel_w"].shape[0]), F32)
+        self.encoded = np.full((self.EL, self.EW), -1.0, F32)
+        self.state[:] = 0.0
+
+    def __call__(self, chunk, is_active):
+        x = int16_to_float(chunk)
+        y = pre_emphasis(x, self.a, self.prev_sample)
+        self.prev_sample = float(x[-1])
+        self.pending = np.concatenate([self.pending, y])
+        while self.pending.shape[0] >= FFT:
+            if is_active:
+                mel = mel_from_magnitude(stft_magnitude(self.pending[None, :FFT]), self.w)[0]
+                self.frames = np.concatenate([self.frames[1:], mel[None]])
+                enc, self.state = self.enc(self.frames[None], self.state)
+                self.encoded = np.concatenate([self.encoded[1:], np.asarray(enc, F32).reshape(1, self.EW)])
+            self.pending = self.pending[HOP:]
+        events = []
+        if not is_active and self.was_active:
+            post = self.det(self.encoded[None])[0][0]
+            k = int(np.argmax(post))
+            events.append(("recognize", k, float(post[k])) if post[k] >= self.thr else ("timeout", -1, 0.0))
+            self.reset()
+        self.was_active = is_active
+        return events

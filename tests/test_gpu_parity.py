@@ -697,6 +697,47 @@ def test_device_pipeline_state_machine_replays_reference_run(wname, name):
     pipe.close()
 
 
+def test_keyword_recognizer_dropin_replays_reference_run():
+    """the KeywordRecognizer drop-in (mel frames from the CUDA filter kernel with pre-emphasis 0.97,
+    the reference's window / state / event logic) against the golden run of the reference's own class with the same
+    stand-in keyword model pair (the reference ships no keyword model), and the constructor's error behaviour."""
+    import os
+    import sys
+    from conftest import GOLDEN, WEIGHTS
+    sys.path.insert(0, GOLDEN)
+    import keyword_stub as KS
+    from wakeword_detection_b200.context import SpeechContext
+    from wakeword_detection_b200.keyword import KeywordRecognizer
+    g = np.load(os.path.join(GOLDEN, "reference_keyword.npz"))
+    d = os.path.join(WEIGHTS, "CRNN")
+    classes = ["up", "down", "stop"]
+    rec = KeywordRecognizer(classes=classes, model_dir=d, posterior_threshold=float(g["kw_threshold"]),
+                            encode_model=KS.Encode(), detect_model=KS.Detect())
+    assert (rec.mel_length, rec.mel_width, rec.encode_length, rec.encode_width) == (12, 40, 5, 6)
+    ctx = SpeechContext()
+    events = []
+    ctx.add_handler("recognize", lambda c: events.append(("recognize", c.transcript, float(c.confidence))))
+    ctx.add_handler("timeout", lambda c: events.append(("timeout", "", 0.0)))
+    pcm, active = g["kw_pcm"], g["kw_active"]
+    frames = []
+    for i in range(len(active)):
+        ctx.is_active = bool(active[i])
+        n0 = len(events)
+        rec(ctx, pcm[i * 320:(i + 1) * 320])
+        frames += [i] * (len(events) - n0)
+        assert np.abs(rec._encoded - g["kw_enc_window"][i]).max() < 1e-3, i
+    assert frames == list(g["kw_event_frame"])
+    assert [e[0] for e in events] == list(g["kw_event_kind"]) and [e[1] for e in events] == list(g["kw_event_class"])
+    assert np.abs(np.array([e[2] for e in events]) - g["kw_event_conf"]).max() < 1e-3
+    with pytest.raises(ValueError):
+        KeywordRecognizer(classes=classes, model_dir=d)                     # no keyword encoder family in the library
+    with pytest.raises(ValueError):
+        KeywordRecognizer(classes=["a", "b"], model_dir=d, encode_model=KS.Encode(), detect_model=KS.Detect())
+    with pytest.raises(ValueError):
+        KeywordRecognizer(classes=classes, model_dir=d, fft_window_type="hamming", encode_model=KS.Encode(), detect_model=KS.Detect())
+    rec.close()
+
+
 def test_tflite_model_and_filter_dropins(golden, w_crnn):
     import os
     from conftest import WEIGHTS

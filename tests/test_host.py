@@ -432,3 +432,51 @@ def test_load_wav_range(tmp_path):
             want[lo - a:hi - a] = whole[lo:hi]
         np.testing.assert_array_equal(EM.load_wav_range(tmp_path / "y.wav", a, b, 16000), want)
         np.testing.assert_array_equal(EM.load_wav_range(whole, a, b, 16000), want)
+
+
+def test_wfst_smoothing_is_the_lattice_shortest_path():
+    """wwdetect/wfst.py:17-71 on the reference's own two test posteriors (:75-97): the Viterbi recursion equals the
+    brute-force minimum over all 2^10 label paths of the lattice the reference builds (pynini cannot run here)."""
+    import itertools
+    from wakeword_detection_b200 import wfst
+    t1 = [[0.8, 0.2], [0.9, 0.1], [0.5, 0.5], [0.4, 0.6], [0.2, 0.8], [0.6, 0.4], [0.3, 0.7], [0.4, 0.6], [0.5, 0.5], [0.9, 0.1]]
+    t2 = [[0.8, 0.2], [0.9, 0.1], [0.5, 0.5], [0.55, 0.45], [0.2, 0.8], [0.6, 0.4], [0.7, 0.3], [0.8, 0.2], [0.3, 0.7], [0.9, 0.1]]
+    for probs in (t1, t2):
+        obs = -np.log(np.array(probs))
+        best, best_cost = None, np.inf
+        for path in itertools.product((0, 1), repeat=len(probs)):
+            c = -np.log(0.5) + obs[0, path[0]]
+            for t in range(1, len(probs)):
+                c += obs[t, path[t]] - (1.0 if path[t] == path[t - 1] else 0.0)
+            if c < best_cost - 1e-12:
+                best, best_cost = list(path), c
+        got, cost = wfst.best_path(probs)
+        assert got == best and abs(cost - best_cost) < 1e-9
+    # the stay bonus keeps the path in the wake-word state through the single contrary frame of test 1 and out of it in test 2
+    assert wfst.smooth(t1) == "other other other wakeword wakeword wakeword wakeword wakeword other other"
+    assert wfst.smooth(t2) == " ".join(["other"] * 10)        # the errant single wake-word frame is smoothed away
+
+
+def test_keyword_oracle_replays_reference_run():
+    """tests/golden/reference_keyword.npz = the reference's own KeywordRecognizer over 5 s of audio with scripted
+    activations (make_golden_keyword.py): the oracle's restatement produces the same events at the same frames and the
+    same encode windows."""
+    import os
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import keyword_stub as KS
+    from oracle import restated as R
+    g = np.load(os.path.join(GOLDEN, "reference_keyword.npz"))
+    o = R.KeywordOracle(load_weights_host("CRNN"), KS.Encode(), KS.Detect(), threshold=float(g["kw_threshold"]))
+    pcm, active = g["kw_pcm"], g["kw_active"]
+    events, frames = [], []
+    for i in range(len(active)):
+        ev = o(pcm[i * 320:(i + 1) * 320], bool(active[i]))
+        events += ev
+        frames += [i] * len(ev)
+        assert np.abs(o.encoded - g["kw_enc_window"][i]).max() < 1e-4, i
+    assert frames == list(g["kw_event_frame"])
+    assert [e[0] for e in events] == list(g["kw_event_kind"])
+    classes = ["up", "down", "stop"]
+    assert [classes[e[1]] if e[1] >= 0 else "" for e in events] == list(g["kw_event_class"])
+    assert np.abs(np.array([e[2] for e in events]) - g["kw_event_conf"]).max() < 1e-4
