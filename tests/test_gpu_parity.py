@@ -570,14 +570,44 @@ def test_eval_counts_time_chunks_sum_to_whole(golden):
         np.testing.assert_array_equal(total, whole)
 
 
+def test_plot_eval_models_process_results_dropin(golden):
+    """utils/plot_eval_models.py:84-129: the 491-threshold sweep of `process_results` from one pass of the counter kernels
+    equals the reference's own `threshold_accepts` loop on the golden trajectory (pm_accepts) and the FRR definition."""
+    from wakeword_detection_b200 import plot_eval_models as PM
+    eng = get_engine("CRNN")
+    traj = golden["pm_traj"]                                   # an (already smooth) trajectory in [0, 1]
+    rng = np.random.default_rng(8)
+    wake = rng.random(333).astype(np.float32)
+    res = PM.process_results({"CRNN": {"wakeword": wake, "smooth_not_wakeword": traj}}, 333, 2.5, engine=eng)["CRNN"]
+    thr = golden["pm_thr"]
+    np.testing.assert_array_equal(res["thresholds"], thr)
+    traj32 = traj.astype(np.float32).astype(np.float64)        # the kernel reads float32 posteriors
+    acc = np.array([PM.threshold_accepts(traj32, t) for t in thr])
+    assert res["FAR"] == sorted((acc / 2.5).tolist())
+    assert res["FRR"] == sorted(((333 - np.array([(wake > t).sum() for t in thr])) / 333).tolist())[::-1]
+    assert res["smooth_FAR"].shape == (462,) and res["smooth_FRR"].shape == (462,)
+    for t in (0.5, 0.7, 0.9):
+        assert PM.threshold_accepts(traj32, t, engine=eng) == PM.threshold_accepts(traj32, t)
+    same = np.array([PM.threshold_accepts(traj, t) for t in thr])
+    assert (same == golden["pm_accepts"]).all()                # the host form is the reference's loop
+
+
 def test_eval_counts_errors():
     eng = get_engine("CRNN")
     with pytest.raises(ValueError):
         eng.eval_counts(np.zeros(10, np.float32), [0, 5, 5, 10], [0.5, 0.6], "frr_max")     # empty clip
     with pytest.raises(ValueError):
         eng.eval_counts(np.zeros(10, np.float32), [0, 10], [0.6, 0.5], "far_edges")         # unsorted
-    with pytest.raises(ValueError):
-        eng.eval_counts(np.zeros(10, np.float32), [0, 10], [0.5], "far_edges")              # shorter than window
+    # a trajectory shorter than the smoothing window: np.convolve(..., 'same') swaps its operands and returns 30 values
+    short = np.array([0.9, 0.95, 0.2, 0.99, 0.97, 0.1, 0.1, 0.98, 0.9, 0.96], np.float32)
+    thr = np.array([0.1, 0.2, 0.25, 0.3, 0.5])
+    sm = np.convolve(short, np.ones(30) / 30, mode="same")
+    assert sm.size == 30
+    want = np.array([R.rising_edges(sm, t) for t in thr])
+    np.testing.assert_array_equal(eng.eval_counts(short, [0, 10], thr, "far_edges").cpu().numpy(), want)
+    both = np.concatenate([short, np.linspace(0, 1, 50).astype(np.float32)])
+    want2 = want + np.array([R.rising_edges(R.smooth_same(both[10:]), t) for t in thr])
+    np.testing.assert_array_equal(eng.eval_counts(both, [0, 10, 60], thr, "far_edges").cpu().numpy(), want2)
 
 
 # ------------------------------------------------------------------------------------ drop-ins

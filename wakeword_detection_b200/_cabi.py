@@ -435,8 +435,16 @@ class Engine:
         if m == WWB_COUNT_FRR_MAX and np.any(np.diff(seg) == 0):
             # np.max([]) in the reference (evaluate_models.py:99)
             raise ValueError("zero-size array to reduction operation maximum which has no identity")
-        if m == WWB_COUNT_FAR_EDGES and nseg and np.any(np.diff(seg) < smooth):
-            raise ValueError("FAR trajectory shorter than the %d-tap smoothing window" % smooth)
+        if m == WWB_COUNT_FAR_EDGES and nseg and smooth > 1 and np.any((np.diff(seg) < smooth) & (np.diff(seg) > 0)):
+            # np.convolve(p, ones(w)/w, 'same') on a trajectory SHORTER than the window swaps its operands and returns
+            # max(M, N) = w values (evaluate_models.py:188-189): rare, so those segments are smoothed here in float64
+            # exactly like numpy and the whole batch goes through the kernel unsmoothed (smooth = 1)
+            if halo_lo is not None or halo_hi is not None:
+                raise ValueError("time-chunk halos need chunks of at least %d posteriors" % smooth)
+            ph = (post.detach().cpu().numpy() if isinstance(post, t.Tensor) else np.asarray(post)).reshape(-1).astype(np.float64)
+            parts = [np.convolve(ph[a:b], np.ones((smooth,)) / smooth, mode='same') for a, b in zip(seg[:-1], seg[1:])]
+            seg = np.concatenate([[0], np.cumsum([x.size for x in parts])]).astype(np.int64)
+            return self._far_edges_f64(np.concatenate(parts) if parts else np.zeros((0,)), seg, thr)
         p = self._dev(post, t.float32).reshape(-1)
         n_total = int(seg[-1])
         if n_total > p.numel():
@@ -451,6 +459,16 @@ class Engine:
             d_lo.data_ptr() if d_lo is not None else None, d_hi.data_ptr() if d_hi is not None else None,
             n_total, d_thr.data_ptr(), int(thr.size), m, int(smooth), counts.data_ptr(), self._stream()))
         return counts
+
+    def _far_edges_f64(self, smoothed: np.ndarray, seg: np.ndarray, thr: np.ndarray):
+        """Rising-edge counts of already smoothed float64 trajectories (host; only for the short-trajectory corner of
+        eval_counts - the values would lose their float64 smoothing if they went back through the float32 kernel)."""
+        counts = np.zeros((thr.size,), np.int64)
+        for a, b in zip(seg[:-1], seg[1:]):
+            x = smoothed[a:b]
+            above = x[None, :] > thr[:, None]
+            counts += np.count_nonzero(above & ~np.concatenate([np.zeros((thr.size, 1), bool), above[:, :-1]], axis=1), axis=1)
+        return self.torch.from_numpy(counts).to(self.device)
 
     # -- streaming ------------------------------------------------------------------------
     def stream_alloc(self, max_streams: int, max_chunk: int) -> None:
