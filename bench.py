@@ -142,7 +142,8 @@ def cpu_reference_rate(models, n_streams, seconds_per_stream, processes):
 
 
 def measured_traffic(kernel, S, N):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (taken at 512 streams; the
+    traffic is per stream, so it is scaled to the step's stream count)
     (profiles/r1_traffic.json); only valid for the shape it was captured on."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(kernel)
