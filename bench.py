@@ -652,9 +652,9 @@ def main():
                                                "executed_TFLOPs": S * nwin["Wavenet"] * exe / (per["Wavenet"] / 1e3) / 1e12}
 
     if rank == 0 and models and not args.no_extras:
-        dev_step()
+        step(pcm_dev[0])                     # (no collective here: the other ranks are not in this branch)
         torch.cuda.synchronize()
-        extra["parity"] = parity_report(engines, models, pcm_dev[(step_no["i"] - 1) % NB], post, thr, S)
+        extra["parity"] = parity_report(engines, models, pcm_dev[0], post, thr, S)
     if rank == 0 and not args.no_extras and args.workload == "sweep":
         del pcm_dev
         torch.cuda.empty_cache()
