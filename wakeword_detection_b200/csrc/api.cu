@@ -229,6 +229,9 @@ static int build_wavenet(wwb_ctx* ctx, const wwb_weights* w) {
   if ((rc = upload(ctx, gb, &N.gate_b))) return rc;
   if ((rc = upload(ctx, rw, &N.rs_w))) return rc;
   if ((rc = upload(ctx, rb, &N.rs_b))) return rc;
+  memcpy(N.h_det1_b, w->det1_b, sizeof(N.h_det1_b));
+  memcpy(N.h_det2_w, w->det2_w, sizeof(N.h_det2_w));
+  memcpy(N.h_det2_b, w->det2_b, sizeof(N.h_det2_b));
   if ((rc = upload(ctx, transposed(w->det1_w, 32, 32), &N.det1_w))) return rc;
   if ((rc = upload(ctx, std::vector<float>(w->det1_b, w->det1_b + 32), &N.det1_b))) return rc;
   if ((rc = upload(ctx, std::vector<float>(w->det2_w, w->det2_w + 64), &N.det2_w))) return rc;

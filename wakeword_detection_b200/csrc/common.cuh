@@ -68,6 +68,7 @@ struct WavenetWeights {
   float* det2_b = nullptr;
   unsigned char* tc_blocks = nullptr;   // tensor-core path: per-block packed weights (wavenet_tc.cu)
   unsigned char* tc_head = nullptr;     // resident head blob
+  float h_det1_b[32] = {}, h_det2_w[64] = {}, h_det2_b[2] = {};   // host copies: kernel parameters of the tensor-core path
 };
 
 struct StreamState {

@@ -123,6 +123,10 @@ struct WnTcParams {
   int join[WN_NT];              // first block tile i takes part in (0 = from the input layer)
   int src_slot[WN_NT];          // snapshot slot a joining tile starts from (-1: input layer x0, skip = 0)
   int snap_slot[24];            // stream mode: snapshot slot written after block k (-1: none)
+  // detect head constants of the 32 -> 2 layer: read as kernel parameters (constant bank, uniform datapath) - as
+  // broadcast shared-memory loads they were ~100 wavefronts per warp and group, with all tiles reaching the detect
+  // epilogue at about the same time (1900 clk of the ~4900 clk group boundary)
+  float det1_b[32], det2_w[64], det2_b[2];
   float* snap;                  // [n_slots][n_rows][WN_SNAP_F]
   int64_t n_rows;               // rows behind x0 / snap (n_streams * ring)
   float* enc_out;
@@ -493,23 +497,20 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         for (int h8 = 0; h8 < 4; ++h8) {
           float d[8];
           tmem_ld8(tbase + WN_C_R + h8 * 8, d);
-          const ulonglong2* b1 = reinterpret_cast<const ulonglong2*>(sm.head.det1_b + h8 * 8);
-          const ulonglong2* w0 = reinterpret_cast<const ulonglong2*>(sm.head.det2_w + h8 * 8);
-          const ulonglong2* w1 = reinterpret_cast<const ulonglong2*>(sm.head.det2_w + 32 + h8 * 8);
-          const ulonglong2 b1a = b1[0], b1b = b1[1], w0a = w0[0], w0b = w0[1], w1a = w1[0], w1b = w1[1];
           tmem_ld_wait();
-          const u64 e0 = relu2(fadd2(pk(d[0], d[1]), b1a.x)), e1 = relu2(fadd2(pk(d[2], d[3]), b1a.y));
-          const u64 e2 = relu2(fadd2(pk(d[4], d[5]), b1b.x)), e3 = relu2(fadd2(pk(d[6], d[7]), b1b.y));
-          acc0[0] = ffma2(w0a.x, e0, acc0[0]); acc0[1] = ffma2(w0a.y, e1, acc0[1]);
-          acc0[0] = ffma2(w0b.x, e2, acc0[0]); acc0[1] = ffma2(w0b.y, e3, acc0[1]);
-          acc1[0] = ffma2(w1a.x, e0, acc1[0]); acc1[1] = ffma2(w1a.y, e1, acc1[1]);
-          acc1[0] = ffma2(w1b.x, e2, acc1[0]); acc1[1] = ffma2(w1b.y, e3, acc1[1]);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int c = h8 * 8 + 2 * p;
+            const u64 e = relu2(fadd2(pk(d[2 * p], d[2 * p + 1]), pk(P.det1_b[c], P.det1_b[c + 1])));
+            acc0[p & 1] = ffma2(pk(P.det2_w[c], P.det2_w[c + 1]), e, acc0[p & 1]);
+            acc1[p & 1] = ffma2(pk(P.det2_w[32 + c], P.det2_w[32 + c + 1]), e, acc1[p & 1]);
+          }
         }
         float fa, fb;
         upk(fadd2(acc0[0], acc0[1]), fa, fb);
-        z0 = (fa + fb) + sm.head.det2_b[0];
+        z0 = (fa + fb) + P.det2_b[0];
         upk(fadd2(acc1[0], acc1[1]), fa, fb);
-        z1 = (fa + fb) + sm.head.det2_b[1];
+        z1 = (fa + fb) + P.det2_b[1];
       }
       fence_before_sync();
       const int zp = (int)(n_u & 1);
@@ -889,6 +890,9 @@ int wavenet_tc_posteriors(wwb_ctx* ctx, const WinMap& wm, float* enc_out, float*
   P.nsplit = ctx->precision == WWB_PREC_TC ? 3 : 1;
   for (int b = 0; b < 24; ++b) { P.dil[b] = ctx->wn.dilation[b]; P.snap_slot[b] = -1; }
   for (int i = 0; i < WN_NT; ++i) { P.join[i] = 0; P.src_slot[i] = -1; }
+  memcpy(P.det1_b, ctx->wn.h_det1_b, sizeof(P.det1_b));
+  memcpy(P.det2_w, ctx->wn.h_det2_w, sizeof(P.det2_w));
+  memcpy(P.det2_b, ctx->wn.h_det2_b, sizeof(P.det2_b));
   P.n_rows = n_rows;
   P.dbg = reinterpret_cast<long long*>(ctx->debug_buf);
   const size_t smem = sizeof(WnSmem) + 128;
