@@ -918,7 +918,6 @@ def test_wavenet_shared_activations_bit_identical_to_per_window_path(S, F, hop):
         os.environ["WWB_WN_NO_SHARE"] = "0"
     b = tc.posteriors(X, hop=hop).clone()
     assert float((a - f32.posteriors(X, hop=hop)).abs().max()) < 1e-4
-    assert float((a - b).abs().max()) < 1e-5
     assert bool((a == b).all())
 
 
