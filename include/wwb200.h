@@ -18,7 +18,11 @@
  *    available from wwb_last_error().  There is no CPU fallback: without a CUDA
  *    device wwb_create fails with WWB_ERR_CUDA.
  *  - a ctx is bound to one device and is not re-entrant (the reference's TFLite
- *    Interpreter is not thread-safe either); distinct ctxs are independent.
+ *    Interpreter is not thread-safe either); distinct ctxs are independent.  Its scratch
+ *    workspaces (mel, encoder intermediates, counters) are per ctx, not per stream: all
+ *    calls on one ctx must be STREAM-ORDERED on one CUDA stream (or separated by
+ *    wwb_sync); growing a workspace synchronises the device.  The *_host entry points use
+ *    three streams owned by the ctx and are ordered among themselves.
  */
 #ifndef WWB200_H
 #define WWB200_H
