@@ -41,7 +41,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale(LIB, deps):
         return LIB
     objs = []
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("NVCC_EXTRA", "").split()
     procs = []
     for s in srcs:
         o = os.path.join(CSRC, os.path.basename(s)[:-3] + ".o")
