@@ -1,3 +1,4 @@
+# needs a library built with NVCC_EXTRA=-DWWB_TIMELINE python -m wakeword_detection_b200.build --force
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

@@ -97,7 +97,11 @@ struct CaParams {
   long long* dbg;               // optional issuer timeline of the CTA's second tile: [20 f][8 events]
 };
 
+#ifdef WWB_TIMELINE   // NVCC_EXTRA=-DWWB_TIMELINE python -m wakeword_detection_b200.build --force (tools/ca_timeline.py); off by default
 #define CA_DBG(f, ev) do { if (P.dbg && blockIdx.x == 0 && tcount == 1 && lane == 0) P.dbg[(f) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define CA_DBG(f, ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ void split8v(const float (&x)[8], uint4& hi, uint4& lo) {
   split_pair(x[0], x[1], hi.x, lo.x);

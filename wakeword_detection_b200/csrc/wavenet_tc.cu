@@ -78,7 +78,7 @@ struct WnSmem {
 #else
 #define WN_DBG2(k, ev) do { } while (0)
 #endif
-#ifdef WWB_WN_TIMELINE   // NVCC_EXTRA=-DWWB_WN_TIMELINE python -m wakeword_detection_b200.build --force, for tools/wn_timeline*.py.
+#ifdef WWB_TIMELINE   // NVCC_EXTRA=-DWWB_TIMELINE python -m wakeword_detection_b200.build --force, for tools/wn_timeline*.py.
                           // Off by default: compiled in, the stamps kept `grp` and the debug pointer live through the block loop and
                           // cost 11 % of the kernel (86.5 -> 76.9 ms per 2560-stream step)
 #define WN_DBG(role, k, ev) do { if (P.dbg && blockIdx.x == 0 && (grp == (int64_t)gridDim.x || grp == 2 * (int64_t)gridDim.x)) P.dbg[((role) * 48 + (k) + (grp == (int64_t)gridDim.x ? 0 : 24)) * 4 + (ev)] = clock64(); } while (0)
