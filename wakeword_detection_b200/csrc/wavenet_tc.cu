@@ -229,7 +229,6 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       const bool valid_g = valid;             // (fetch_state of the next group overwrites `valid` before the detect epilogue)
       const bool snap_g = snap_out;
       float* const snap_g_dst = snap_dst;
-      const int64_t b_g = b;
       // ---- start state -> U row (operand of the first gate GEMM); that block's BatchNorm is folded into its gate weights ----
       {
         if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 0);
@@ -383,7 +382,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       }
 
       if (P.enc_out && valid_g) {
-        float4* dst = reinterpret_cast<float4*>(P.enc_out + (b_g * L + t) * 32);
+        float4* dst = reinterpret_cast<float4*>(P.enc_out + ((grp * WN_G + w) * L + t) * 32);
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
           float s0, s1, s2, s3;
