@@ -645,8 +645,13 @@ def main():
                                         "columns_per_window": cols / nwin["CRNN"]}
     if "Wavenet" in models and args.precision != "f32" and nwin["Wavenet"] >= 8:
         # Sliding windows take every activation outside the causal-padding cone from a stream-level pass
-        # (wavenet_tc.cu): 62 of 120 tile-blocks per group of 3 windows + 24 blocks per 460 stream frames are executed.
-        frac = 62.0 / 120.0 + (F / 460.0) * 120.0 / (nwin["Wavenet"] / 3.0 * 120.0)
+        # (wavenet_tc.cu): groups of 4 windows = 6 tiles of 128 time-major rows, tile i joins at the first block whose
+        # padding-dependent prefix D(b) = sum 2*dilation reaches its first time step; the stream pass runs all 24 blocks
+        # on chunks of 768 frames that advance by 588.  Fraction = executed rows x blocks / (182 x 24) per window.
+        G, NT, L_wn = 4, 6, 182
+        D = np.cumsum(2 * np.tile([1, 2, 4, 8], 6))
+        tile_blocks = sum(24 - int(np.argmax(D > (128 * i) // G)) for i in range(NT))          # 76
+        frac = (tile_blocks * 128.0 / G + (F / (NT * 128.0 - 180.0)) * NT * 24 * 128.0 / nwin["Wavenet"]) / (L_wn * 24.0)
         exe = FLOP_PER_WINDOW["Wavenet"] * frac
         extra["Wavenet_shared_activations"] = {"executed_fraction_of_tile_blocks": frac,
                                                "executed_TFLOPs": S * nwin["Wavenet"] * exe / (per["Wavenet"] / 1e3) / 1e12}

@@ -637,6 +637,12 @@ __device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
 
 __device__ __forceinline__ void tmem_ldN(uint32_t taddr, float (&v)[8]) { tmem_ld8f(taddr, v); }
 __device__ __forceinline__ void tmem_ldN(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+// A/B switch (tools/build_variant.sh): the recurrence kernels' issuing warp busy-polls the barriers on the per-step chain
+#ifdef WWB_GR_ISS_SPIN
+#define GR_ISS_WAIT(bar, par) do { while (!mbar_test_wait(bar, par)) { } } while (0)
+#else
+#define GR_ISS_WAIT(bar, par) mbar_wait(bar, par)
+#endif
 #ifndef GR_CHUNKS
 #define GR_CHUNKS 2                                // the epilogue processes the 32 units in this many pieces (2: 2.94 -> 2.90 ms CRNN stage against 4)
 #endif
@@ -815,7 +821,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
         for (int d = 0; d < 2; ++d) {
           load_next(0);
           load_next(1);
-          mbar_wait(&sm.h_ready[d], n_h & 1);
+          GR_ISS_WAIT(&sm.h_ready[d], n_h & 1);
           fence_after_sync();
           if (elect_one()) {
             const uint32_t acc = tmem + d * 96, ta = tmem + 192 + d * 32;
@@ -1065,7 +1071,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru2_fused_tc_kernel(const G2Pa
           load_next(1);
           const int xs = n_step % G2_AST;
           mbar_wait(&sm.a_full[d][xs], (n_step / G2_AST) & 1);
-          if (n_step > 0) mbar_wait(&sm.acc_free[d], (n_step - 1) & 1);
+          if (n_step > 0) GR_ISS_WAIT(&sm.acc_free[d], (n_step - 1) & 1);
           fence_after_sync();
           if (elect_one()) {
             const uint32_t acc = tmem + d * 128;
@@ -1091,7 +1097,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru2_fused_tc_kernel(const G2Pa
         for (int d = 0; d < 2; ++d) {
           load_next(0);
           load_next(1);
-          mbar_wait(&sm.h_ready[d], n_h & 1);
+          GR_ISS_WAIT(&sm.h_ready[d], n_h & 1);
           fence_after_sync();
           if (elect_one()) {
             const uint32_t acc = tmem + d * 128, ta = tmem + TM_H + d * 32;

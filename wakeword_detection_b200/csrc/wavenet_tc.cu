@@ -1,18 +1,20 @@
 // K5/K6 — WaveNet encode + detect on the tensor cores (precision WWB_PREC_TC / TC_FAST).
 //
-// One persistent CTA per SM processes groups of WN_G = 3 windows.  The rows of a group are interleaved
-// TIME-MAJOR: (time t, window w) -> o = t*3 + w form the M dimension of every GEMM (5 tiles of 128 rows, 546 of the
-// 640 rows are real; the 48 rows in front of row 0 are the causal zero padding of all three windows).  A dilated tap
-// is still a linear row shift (3*d rows).  Each of the 640 epilogue threads owns ONE row for the whole 24-block
-// stack: its 16-channel residual stream and 32-channel skip sum never leave registers.
+// One persistent CTA per SM processes groups of WN_G = 4 windows.  The rows of a group are interleaved
+// TIME-MAJOR: (time t, window w) -> o = t*4 + w form the M dimension of every GEMM (6 tiles of 128 rows, 728 of the
+// 768 rows are real; the 64 rows in front of row 0 are the causal zero padding of all four windows).  A dilated tap
+// is still a linear row shift (4*d rows).  Each of the 768 epilogue threads owns ONE row for the whole 24-block
+// stack: its 16-channel residual stream and 32-channel skip sum never leave registers.  (Round 2 ran 3 windows on
+// 5 tiles at 80 registers per thread; 4 on 6 - 832 threads, 72 registers, 80 instead of 96 tensor-memory columns per
+// tile - pays the per-block dependency chain once per 4 windows instead of 3: 15.5 -> 13.9 ms per 512 x 10 s.)
 //
 // SHARED ACTIVATIONS (sliding-window batches).  Row t of block b depends on the window's zero padding only while
 // t < D(b) = sum_{m<=b} 2*dilation[m] (2, 6, 14, 30, 32, ... 180): every other activation is a function of the
 // stream's absolute frame and identical in all ~91 windows that cover it.  With time-major rows the window-dependent
 // ("dirty") rows of a block are a PREFIX, so tile i only has to take part from block join[i] = min{b : D(b) > t_min(i)}
-// on (0, 6, 11, 18, 23 for the shipped model: 62 instead of 120 tile-blocks per group).  A tile joins from per-frame
+// on (0, 5, 9, 14, 18, 22 for the shipped model: 76 instead of 144 tile-blocks per group).  A tile joins from per-frame
 // SNAPSHOTS (residual stream x and the skip prefix sum after block join[i]-1; 192 B per frame and level) written by a
-// stream-level pass of this same kernel (stream_mode: a group is a chunk of 640 consecutive frames of one stream,
+// stream-level pass of this same kernel (stream_mode: a group is a chunk of 768 consecutive frames of one stream,
 // rows o >= 180 of a chunk are past every receptive field; +1.5 % work).  Same MMAs on the same operand values in the
 // same order, so the posteriors are bit-identical to the per-window formulation (WWB_WN_NO_SHARE=1 forces it).
 // Per block and tile:
@@ -22,8 +24,9 @@
 //               tap 2 (no shift) reads A straight from TENSOR MEMORY, where the row's owner
 //               thread stored it (tcgen05.st): 15.5 clk per MMA instead of 39.4 (tools/tc_rate_probe.cu)
 //   epilogue 1  g = tanh(.)*sigmoid(.) (2 ex2 per channel, 1 rcp per channel pair), fp16 hi/lo -> TMEM, over the
-//               consumed gate accumulator (A operand of the next GEMM)
-//   res/skip    D[128,48] = g[128,16] * [Wres | Wskip]       (A from TMEM, own accumulator columns)
+//               consumed gate accumulator (A operand of the next GEMM), half by half
+//   res/skip    D[128,48] = g[128,16] * [Wres | Wskip]       (A from TMEM; res lands on the consumed second half of
+//               the gate accumulator, skip on its own 32 columns)
 //   epilogue 2a x += ReLU(res); u = BN_next(x) -> hi/lo -> shared memory + TMEM   (releases the next gate GEMM)
 //   epilogue 2b skip += ReLU(.)                                                   (overlaps that GEMM)
 // The input 1x1 conv depends only on the mel row, which ~91 overlapping windows share: wn_input_kernel computes it once
@@ -36,20 +39,27 @@
 // The per-block BatchNorm affine u = bn_mul * x + bn_add is FOLDED into the gate GEMM (weights * bn_mul, bias +
 // W * bn_add), so the A operand is the residual stream x itself and the epilogue neither loads the 32 constants
 // (8 broadcast LDS.128 = 32 shared-memory wavefronts per warp and block, 17 % of the shared-memory pipe) nor
-// applies them.  The causal zero padding is of u, not x: the 48 padding rows in front of row 0 therefore
-// hold x_pad = -bn_add / bn_mul (so that u_pad = 0), rewritten for each block by the threads of rows 0..47.
+// applies them.  The causal zero padding is of u, not x: the padding rows in front of row 0 therefore
+// hold x_pad = -bn_add / bn_mul (so that u_pad = 0), rewritten for each block by the res/skip warp.
 // fp16 hi/lo operand split (3 MMAs per product) keeps the result at fp32 accuracy
 // (DESIGN.md §precision).  Epilogue arithmetic uses the packed fp32x2 instructions (FFMA2/FADD2).
-// Per-block weights (12 KB incl. the bias operands) stream through a 4-stage cp.async.bulk ring.
+// Per-block weights (12 KB incl. the bias operands) stream through a 6-stage cp.async.bulk ring.
+// The U rows (A operand of the shifted taps) are double-buffered by block parity: level k is read from buffer k & 1
+// and level k+1 written to the other, so no epilogue ever waits for a neighbouring tile's GEMM to finish reading.
 //
 // GEMM issue: one extra warp issues the gate GEMMs tile after tile (in order, so they run back to back and
 // stagger the tiles: the tensor pipe, the SFU and the FMA/ALU pipes then work on different tiles at the
-// same time); a second extra warp issues the small res/skip GEMMs, so they never queue behind a wait of the
-// gate warp.  Epilogue 2 is split: 2a (residual -> u) releases the next gate GEMM, 2b (skip sum) overlaps it.
+// same time); a second extra warp issues the small res/skip GEMMs and the detect GEMMs, so they never queue behind a
+// wait of the gate warp.  Both busy-poll their barriers (their wake-up latency is on every tile's chain).
+// Epilogue 2 is split: 2a (residual -> u) releases the next gate GEMM, 2b (skip sum) overlaps it.
 // Ordering rules:
-//   gate(k,i) needs epilogue 2 of (k-1,i) and (k-1,i-1)      (its taps reach up to 48 rows into tile i-1)
-//   rs(k,i)   needs epilogue 1 of (k,i) and gate(k,i+1) COMPLETE: epilogue 2 of (k,i) overwrites rows that
-//             GEMM reads, and GEMMs issued by different threads have no implicit order.
+//   gate(k,i) needs epilogue 2 of (k-1,i) and (k-1,i-1)      (its taps reach up to 64 rows into tile i-1)
+//   rs(k,i)   needs epilogue 1 of (k,i)
+//   GEMMs issued by one thread execute in order: gate(k-1, i+1) precedes gate(k, i), so by the time epilogue 2a of
+//   (k, i) writes level k+1 into buffer (k+1) & 1, the last reader of that buffer's level k-1 has completed.
+// Group boundary: no CTA barrier and no in-order wait - a tile hands the next group's start state to the gate warp as
+// soon as it has read its detect accumulator; the gate warp's refill of the weight stage of block 23 is the one
+// thing that has to know that every tile has left the previous group (deferred to block 2, see there).
 #include <string.h>
 
 #include "wavenet_tc.cuh"
@@ -58,7 +68,8 @@ namespace wwb {
 
 
 struct WnSmem {
-  unsigned char U[2 * 2 * WN_PU];          // [plane][chunk][row]
+  unsigned char U[WN_UBUF];                // [plane][chunk][row]
+  float4 skip[8 * WN_ROWS];                // skip sums [channel quad][row]: each thread keeps its row's 32 sums HERE, not in registers (see the kernel)
   unsigned char W[WN_WST][WN_WBLK];
   WnHead head;
   uint64_t bar_gate[WN_NT], bar_rs[WN_NT], bar_det[WN_NT];   // GEMM completion (tcgen05.commit) -> the tile's four warps
@@ -74,7 +85,7 @@ struct WnSmem {
 
 // fine-grained chain stamps of tile 0 (first timed group): [24 blocks][16 events] behind the hang-report area
 #ifdef WWB_WN_DBG2
-#define WN_DBG2(k, ev) do { if (P.dbg && blockIdx.x == 0 && grp == (int64_t)gridDim.x) P.dbg[8 * 48 * 4 + 64 + (k) * 16 + (ev)] = clock64(); } while (0)
+#define WN_DBG2(k, ev) do { if (P.dbg && blockIdx.x == 0 && grp == (int64_t)gridDim.x) P.dbg[WN_DBG_ROLES * 48 * 4 + 64 + (k) * 16 + (ev)] = clock64(); } while (0)
 #else
 #define WN_DBG2(k, ev) do { } while (0)
 #endif
@@ -97,11 +108,11 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 __device__ __noinline__ void wn_hang(long long* dbg, const uint32_t* cnt_u, const uint32_t* cnt_g, int id, int tile, int q,
                                      uint32_t n_gate, uint32_t n_rs, uint32_t n_u, uint32_t n_w) {
   if (dbg) {
-    long long* base = dbg + 8 * 48 * 4;
+    long long* base = dbg + WN_DBG_ROLES * 48 * 4;
     if (atomicCAS(reinterpret_cast<unsigned long long*>(base), 0ull, 1ull) == 0ull) {
       base[1] = id; base[2] = blockIdx.x; base[3] = tile; base[4] = q; base[5] = n_gate; base[6] = n_rs;
       base[7] = n_u; base[8] = n_w;
-      if (cnt_u) for (int i = 0; i < 5; ++i) { base[9 + i] = cnt_u[i]; base[14 + i] = cnt_g[i]; }
+      if (cnt_u) for (int i = 0; i < WN_NT; ++i) { base[9 + i] = cnt_u[i]; base[9 + WN_NT + i] = cnt_g[i]; }
     }
   }
   asm volatile("exit;");
@@ -110,6 +121,21 @@ __device__ __noinline__ void wn_hang(long long* dbg, const uint32_t* cnt_u, cons
 #define WN_MBAR_WAIT(bar, par, id) do { if (!mbar_try_wait(bar, par)) { uint32_t sp_ = 0; while (!mbar_try_wait(bar, par)) if (++sp_ > WN_SPIN_LIMIT) WN_HANG(id); } } while (0)
 #else
 #define WN_MBAR_WAIT(bar, par, id) mbar_wait(bar, par)
+#endif
+// A/B switches (tools/build_variant.sh): busy-poll instead of the suspending try_wait in the epilogue warps / the two issuing warps
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+  while (!mbar_test_wait(bar, parity)) { }
+}
+#ifdef WWB_WN_EPI_SPIN
+#define WN_WAIT_E(bar, par, id) mbar_spin(bar, par)
+#else
+#define WN_WAIT_E(bar, par, id) WN_MBAR_WAIT(bar, par, id)
+#endif
+#ifndef WWB_WN_ISS_SUSPEND
+#define WN_WAIT_I(bar, par, id) mbar_spin(bar, par)
+#else
+#define WN_WAIT_I(bar, par, id) WN_MBAR_WAIT(bar, par, id)
 #endif
 
 __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcParams P) {
@@ -154,6 +180,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     const uint32_t tbase = tacc + ((uint32_t)(q * 32) << 16);         // ... seen from this warp's lane quadrant
     uint32_t n_gate = 0, n_rs = 0, n_u = 0;  // completed phases of bar_gate / bar_rs ; groups done
     unsigned char* const Urow = sm.U + (WN_PAD + o) * 16;
+    float4* const sk = sm.skip + o;           // this row's skip sums: sk[c4 * WN_ROWS], conflict-free 16-byte accesses
     {
       uint32_t one[16];
 #pragma unroll
@@ -171,7 +198,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     // with an empty skip sum, or - for a tile that joins at block jn > 0 - the stream-level snapshot after block jn-1.
     // The state of the NEXT group is fetched straight into x / skip before this group's detect epilogue (both are dead
     // by then), so its global-memory latency is not on the group-boundary chain.
-    u64 x[8], skip[16];     // channel pairs
+    u64 x[8];               // channel pairs
     bool valid = false, snap_out = false;
     int64_t b = 0;
     float* snap_dst = nullptr;
@@ -207,11 +234,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           x[2 * i + 1] = pk(v.z, v.w);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 v = vn ? __ldg(p + 4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          skip[2 * i] = pk(v.x, v.y);
-          skip[2 * i + 1] = pk(v.z, v.w);
-        }
+        for (int i = 0; i < 8; ++i) sk[i * WN_ROWS] = vn ? __ldg(p + 4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
         const float4* p = reinterpret_cast<const float4*>(P.x0 + row * 16);
 #pragma unroll
@@ -221,59 +244,65 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           x[2 * i + 1] = pk(v.z, v.w);
         }
 #pragma unroll
-        for (int n = 0; n < 16; ++n) skip[n] = ZERO2;
+        for (int i = 0; i < 8; ++i) sk[i * WN_ROWS] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
+    // ---- start state -> U row of buffer 0 (operand of the first gate GEMM); that block's BatchNorm is folded into its gate weights ----
+    auto put_start_state = [&]() {
+      uint32_t ur[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) split2(x[i], ur[i], ur[8 + i]);
+      if (valid) {
+        *reinterpret_cast<uint4*>(Urow) = make_uint4(ur[0], ur[1], ur[2], ur[3]);
+        *reinterpret_cast<uint4*>(Urow + WN_PU) = make_uint4(ur[4], ur[5], ur[6], ur[7]);
+        *reinterpret_cast<uint4*>(Urow + 2 * WN_PU) = make_uint4(ur[8], ur[9], ur[10], ur[11]);
+        *reinterpret_cast<uint4*>(Urow + 3 * WN_PU) = make_uint4(ur[12], ur[13], ur[14], ur[15]);
+      }
+      tmem_st16(tbase + WN_C_U, ur);
+      tmem_st_wait();
+      fence_before_sync();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.bar_u[tile]);
+    };
     fetch_state(blockIdx.x);
+    if ((int64_t)blockIdx.x < n_groups) put_start_state();
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++n_u) {
       const bool valid_g = valid;             // (fetch_state of the next group overwrites `valid` before the detect epilogue)
       const bool snap_g = snap_out;
       float* const snap_g_dst = snap_dst;
-      // ---- start state -> U row (operand of the first gate GEMM); that block's BatchNorm is folded into its gate weights ----
-      {
-        if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 0);
-        uint32_t ur[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) split2(x[i], ur[i], ur[8 + i]);
-        if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 21, 1);
-        if (valid_g) {
-          *reinterpret_cast<uint4*>(Urow) = make_uint4(ur[0], ur[1], ur[2], ur[3]);
-          *reinterpret_cast<uint4*>(Urow + WN_PU) = make_uint4(ur[4], ur[5], ur[6], ur[7]);
-          *reinterpret_cast<uint4*>(Urow + 2 * WN_PU) = make_uint4(ur[8], ur[9], ur[10], ur[11]);
-          *reinterpret_cast<uint4*>(Urow + 3 * WN_PU) = make_uint4(ur[12], ur[13], ur[14], ur[15]);
-        }
-        tmem_st16(tbase + WN_C_U, ur);
-        tmem_st_wait();
-        fence_before_sync();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.bar_u[tile]);
-      }
-
       for (int k = jn; k < 24; ++k) {
         // ---- epilogue 1: gated activation ----
-        WN_MBAR_WAIT(&sm.bar_gate[tile], n_gate & 1, 5);
+        WN_WAIT_E(&sm.bar_gate[tile], n_gate & 1, 5);
         ++n_gate;
         fence_after_sync();
         if (q == 0 && lane == 0) WN_DBG(tile, k, 0);
         if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 0);
         {
-          uint32_t gr[16];
+          // The accumulator columns are ordered [tanh 0-7 | sigmoid 0-7 | tanh 8-15 | sigmoid 8-15] (wavenet_pack_blocks), so
+          // each half is consumed by ONE load and its g hi/lo can be stored over it right away: 8 result registers
+          // live instead of 16 (the kernel sits at the register limit of 832 threads)
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8) {
-            float at[8], as[8];
-            tmem_ld8(tbase + h8 * 8, at);
-            tmem_ld8(tbase + 16 + h8 * 8, as);
+            float v[16];
+            tmem_ld16(tbase + h8 * 16, v);
             tmem_ld_wait();
             if (h8 == 0 && tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 1);
+            uint32_t gh[4], gl[4];
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
               // accumulators arrive as a2 = -2*log2(e)*(a + b_t), b2 = -log2(e)*(b + b_s) (scaled weights, bias GEMM)
-              const float a0 = at[2 * p], a1 = at[2 * p + 1], b0 = as[2 * p], b1 = as[2 * p + 1];
+              const float a0 = v[2 * p], a1 = v[2 * p + 1], b0 = v[8 + 2 * p], b1 = v[8 + 2 * p + 1];
               // exponents clamped at 30: tanh is -1 and sigmoid 0 to 1e-9 beyond, and both denominators stay below
               // 2^61, so ONE reciprocal serves the pair of channels (1/d0 = d1/(d0 d1)): 5 SFU ops per pair instead
               // of 6 - the SFU queue is what stretches this epilogue (profiles/r1_notes.md)
+#ifdef WWB_WN_EX2_POLY
+              float ea0, ea1;
+              if (p < WWB_WN_EX2_POLY) ex2_poly2(fminf(a0, 30.f), fminf(a1, 30.f), ea0, ea1);
+              else { ea0 = ex2_approx(fminf(a0, 30.f)); ea1 = ex2_approx(fminf(a1, 30.f)); }
+#else
               const float ea0 = ex2_approx(fminf(a0, 30.f)), ea1 = ex2_approx(fminf(a1, 30.f));
+#endif
               const float eb0 = ex2_approx(fminf(b0, 30.f)), eb1 = ex2_approx(fminf(b1, 30.f));
               const u64 tt = fadd2(pk(eb0, eb1), ONE2);
               float d0, d1;
@@ -281,11 +310,12 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
               const float rp = rcp_approx(d0 * d1);
               const float r0 = rp * d1, r1 = rp * d0;
               const u64 g = pk(fmaf(-ea0, r0, r0), fmaf(-ea1, r1, r1)); // tanh(a) * sigmoid(b)
-              split2(g, gr[h8 * 4 + p], gr[8 + h8 * 4 + p]);
+              split2(g, gh[p], gl[p]);
             }
+            tmem_st4(tbase + WN_C_G + h8 * 4, gh);
+            tmem_st4(tbase + WN_C_G + 8 + h8 * 4, gl);
           }
           if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 2);
-          tmem_st16(tbase + WN_C_G, gr);
           tmem_st_wait();
           if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 3);
         }
@@ -296,34 +326,33 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 4);
 
         // ---- epilogue 2a: residual, next block's BN -> u (releases the next gate GEMM) ----
-        WN_MBAR_WAIT(&sm.bar_rs[tile], n_rs & 1, 6);
+        WN_WAIT_E(&sm.bar_rs[tile], n_rs & 1, 6);
         ++n_rs;
         fence_after_sync();
         if (q == 0 && lane == 0) WN_DBG(tile, k, 2);
         if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 5);
         const bool last = (k == 23);
         if (!last) {
-          uint32_t ur[16];
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8) {
             float r[8];
             tmem_ld8(tbase + WN_C_R + h8 * 8, r);
             tmem_ld_wait();
+            uint32_t uh[4], ul[4];
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
               const int c = h8 * 4 + p;
               x[c] = add_relu2(x[c], pk(r[2 * p], r[2 * p + 1]));
-              split2(x[c], ur[c], ur[8 + c]);   // the next block's BN is folded into its gate weights
+              split2(x[c], uh[p], ul[p]);   // the next block's BN is folded into its gate weights
             }
-          }
-          if (valid_g) {
-            *reinterpret_cast<uint4*>(Urow) = make_uint4(ur[0], ur[1], ur[2], ur[3]);
-            *reinterpret_cast<uint4*>(Urow + WN_PU) = make_uint4(ur[4], ur[5], ur[6], ur[7]);
-            *reinterpret_cast<uint4*>(Urow + 2 * WN_PU) = make_uint4(ur[8], ur[9], ur[10], ur[11]);
-            *reinterpret_cast<uint4*>(Urow + 3 * WN_PU) = make_uint4(ur[12], ur[13], ur[14], ur[15]);
+            if (valid_g) {
+              *reinterpret_cast<uint4*>(Urow + h8 * WN_PU) = make_uint4(uh[0], uh[1], uh[2], uh[3]);
+              *reinterpret_cast<uint4*>(Urow + (2 + h8) * WN_PU) = make_uint4(ul[0], ul[1], ul[2], ul[3]);
+            }
+            tmem_st4(tbase + WN_C_U + h8 * 4, uh);
+            tmem_st4(tbase + WN_C_U + 8 + h8 * 4, ul);
           }
           if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 6);
-          tmem_st16(tbase + WN_C_U, ur);
           tmem_st_wait();
           if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 8);
           fence_before_sync();
@@ -334,13 +363,30 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           if (tile == 0 && q == 0 && lane == 0) WN_DBG2(k, 9);
         }
         // ---- epilogue 2b: skip sum (off the critical path: the next gate GEMM is already running) ----
+        // The 32 sums of a row live in shared memory, not in registers: with 16 + 32 state registers per row the kernel
+        // spilled inside this loop at the 72 registers 832 threads leave; 8 LDS.128 + 8 STS.128 per row and block that
+        // nothing waits for are cheaper.  After the last block the sums in hand become the detect head's input
+        // (ReLU, fp16 hi/lo; channels 0-15 -> the u columns, 16-31 -> the g columns).
 #pragma unroll
         for (int h8 = 0; h8 < 4; ++h8) {
           float s[8];
           tmem_ld8(tbase + WN_C_R + 16 + h8 * 8, s);
+          const float4 c0 = sk[(2 * h8) * WN_ROWS], c1 = sk[(2 * h8 + 1) * WN_ROWS];
           tmem_ld_wait();
-#pragma unroll
-          for (int p = 0; p < 4; ++p) skip[h8 * 4 + p] = add_relu2(skip[h8 * 4 + p], pk(s[2 * p], s[2 * p + 1]));
+          const u64 n0 = add_relu2(pk(c0.x, c0.y), pk(s[0], s[1])), n1 = add_relu2(pk(c0.z, c0.w), pk(s[2], s[3]));
+          const u64 n2 = add_relu2(pk(c1.x, c1.y), pk(s[4], s[5])), n3 = add_relu2(pk(c1.z, c1.w), pk(s[6], s[7]));
+          float4 o0, o1;
+          upk(n0, o0.x, o0.y); upk(n1, o0.z, o0.w); upk(n2, o1.x, o1.y); upk(n3, o1.z, o1.w);
+          sk[(2 * h8) * WN_ROWS] = o0;
+          sk[(2 * h8 + 1) * WN_ROWS] = o1;
+          if (last) {
+            uint32_t eh[4], el[4];
+            split2(relu2(n0), eh[0], el[0]); split2(relu2(n1), eh[1], el[1]);
+            split2(relu2(n2), eh[2], el[2]); split2(relu2(n3), eh[3], el[3]);
+            const uint32_t cx = tbase + (h8 < 2 ? WN_C_U : WN_C_G) + (h8 & 1) * 4;
+            tmem_st4(cx, eh);
+            tmem_st4(cx + 8, el);
+          }
         }
         fence_before_sync();
         if (stream_mode) {
@@ -356,23 +402,10 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
               dst[i] = make_float4(a0, a1, a2, a3);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float a0, a1, a2, a3;
-              upk(skip[2 * i], a0, a1);
-              upk(skip[2 * i + 1], a2, a3);
-              dst[4 + i] = make_float4(a0, a1, a2, a3);
-            }
+            for (int i = 0; i < 8; ++i) dst[4 + i] = sk[i * WN_ROWS];
           }
         }
         if (last) {
-          // detect input: ReLU(skip) hi/lo; channels 0-15 -> the u columns, 16-31 -> the g columns
-          uint32_t er[16];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) split2(relu2(skip[c]), er[c], er[8 + c]);
-          tmem_st16(tbase + WN_C_U, er);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) split2(relu2(skip[8 + c]), er[c], er[8 + c]);
-          tmem_st16(tbase + WN_C_G, er);
           tmem_st_wait();
           fence_before_sync();
           __syncwarp();
@@ -384,19 +417,14 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       if (P.enc_out && valid_g) {
         float4* dst = reinterpret_cast<float4*>(P.enc_out + ((grp * WN_G + w) * L + t) * 32);
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-          float s0, s1, s2, s3;
-          upk(skip[2 * n], s0, s1);
-          upk(skip[2 * n + 1], s2, s3);
-          dst[n] = make_float4(s0, s1, s2, s3);
-        }
+        for (int n = 0; n < 8; ++n) dst[n] = sk[n * WN_ROWS];
       }
-      if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 0);   // boundary timeline: e2b(23) done
+      if (tile == 0 && q == 0 && lane == 0) WN_DBG(WN_NT + 1, 20, 0);   // boundary timeline: e2b(23) done
       fetch_state(grp + gridDim.x);   // next group's start state: in flight during the detect epilogue
       // ---- detect head epilogue: ReLU(D + b1) -> 32->2 -> max over time ----
       WN_MBAR_WAIT(&sm.bar_det[tile], n_u & 1, 8);
       fence_after_sync();
-      if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 1);   // detect GEMM done
+      if (tile == 0 && q == 0 && lane == 0) WN_DBG(WN_NT + 1, 20, 1);   // detect GEMM done
       // 32 -> 2 with 128-bit loads of the constants and four independent partial sums per logit (as 96 scalar loads
       // feeding two 32-long dependent FMA chains this epilogue took ~2500 clk on the group-boundary critical path)
       float z0, z1;
@@ -421,7 +449,11 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         upk(fadd2(acc1[0], acc1[1]), fa, fb);
         z1 = (fa + fb) + P.det2_b[1];
       }
-      fence_before_sync();
+      // the detect accumulator has been read: hand the NEXT group's start state to the gate warp before the reductions
+      // below (they are ~1000 clk of shuffles and shared-memory atomics that the next gate GEMM does not depend on)
+#ifdef WWB_WN_EARLY_START   // (A/B: with the in-order gate warp an early start state buys nothing and delays the reductions: 13.83 vs 13.49 ms)
+      put_start_state();
+#endif
       const int zp = (int)(n_u & 1);
       if (!stream_mode) {
         // a warp's 32 rows are ~11 time steps of all three windows: one reduction + one atomic per window and logit
@@ -438,7 +470,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             }
           }
         }
-        if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 2);   // detect epilogue done
+        if (tile == 0 && q == 0 && lane == 0) WN_DBG(WN_NT + 1, 20, 2);   // detect epilogue done
         // No CTA barrier at the group boundary: the LAST of the 20 warps to add its rows turns the maxima into posteriors
         // and clears them.  zmax / zcnt are double-buffered by group parity; the tiles of a CTA are never more than a few
         // blocks apart (each gate GEMM needs the tile below one block back), so group g + 2 cannot reach this point before
@@ -464,7 +496,10 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         }
         __syncwarp();
       }
-      if (tile == 0 && q == 0 && lane == 0) WN_DBG(6, 20, 3);
+#ifndef WWB_WN_EARLY_START
+      put_start_state();
+#endif
+      if (tile == 0 && q == 0 && lane == 0) WN_DBG(WN_NT + 1, 20, 3);
     }
   } else if (warp == WN_EPI_WARPS) {
     // =========================== gate-GEMM warp + weight loader ===========================
@@ -474,10 +509,12 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
     // gate(k,i) also needs epilogue 2 of (k-1,i-1) (its taps reach 16 rows into tile i-1): awaited one step earlier.
     const int tile = 0, q = 0;   // (for the hang report)
     uint32_t n_gate = 0, n_rs = 0, n_u = 0;
+    (void)tile; (void)q; (void)n_gate; (void)n_rs;
     const uint64_t dU = make_desc(smem_u32(sm.U), WN_PU, 128);                   // U row 0, hi plane
     const uint64_t dWg = make_desc(smem_u32(sm.W[0]), 512, 128);                 // gate B: stage 0, tap 0, hi plane
     const uint64_t dBg = make_desc(smem_u32(sm.W[0]) + WN_OFF_GBIAS, 512, 128);  // gate bias B: stage 0
     const uint64_t dH = make_desc(smem_u32(sm.head.det1_B), 512, 128);           // detect B: k-step 0, hi plane
+    (void)dH;
     uint32_t my_groups = 0;
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) ++my_groups;
     const uint32_t total_loads = my_groups * 24;
@@ -500,12 +537,12 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
 #pragma unroll
         for (int i = 0; i < WN_NT; ++i) {
           if (k < P.join[i]) continue;                   // the tile's rows are still shared (stream-level) activations
-          if (i == 1) WN_DBG(6, k, 0);
+          if (i == 1) WN_DBG(WN_NT + 1, k, 0);
           if (i == 0 && lane == 0) WN_DBG2(k, 10);
-          WN_MBAR_WAIT(&sm.bar_u[i], cu[i] & 1, 2);
+          WN_WAIT_I(&sm.bar_u[i], cu[i] & 1, 2);
           ++cu[i];
           if (i == 0 && lane == 0) WN_DBG2(k, 11);
-          if (i == 1) WN_DBG(6, k, 1);
+          if (i == 1) WN_DBG(WN_NT + 1, k, 1);
           fence_after_sync();
           if (elect_one()) {   // one lane issues the whole tile (uniform descriptors, no per-MMA election)
             const uint32_t tacc = tmem + i * WN_TMEM_TILE;
@@ -529,21 +566,36 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             mma_f16_ts(tacc, tmem + WN_C_ONE, bb, idesc_gate, true);
             mma_commit(&sm.bar_gate[i]);
             if (i == 0) WN_DBG2(k, 12);
-            if (i == 0) WN_DBG(5, k, 0);
-            if (i == WN_NT - 1) WN_DBG(5, k, 1);
+            if (i == 0) WN_DBG(WN_NT, k, 0);
+            if (i == WN_NT - 1) WN_DBG(WN_NT, k, 1);
           }
           __syncwarp();
-          if (i == 1) WN_DBG(6, k, 2);
+          if (i == 1) WN_DBG(WN_NT + 1, k, 2);
         }
-        // every active tile has finished block n_w-1 (its epilogue 2 was awaited above): refill that stage
-        if (n_w >= 1 && n_w - 1 + WN_WST < total_loads) {
-          const uint32_t nl = n_w - 1 + WN_WST;
-          if (lane == 0) {
+        // Every tile that is active in block k has finished block n_w-1 (its epilogue 2 was awaited above): refill that
+        // stage.  Not so at a group's first block: the tiles that join later may still be in block 23 of the previous
+        // group (nobody waits for them at the boundary any more) - that refill is deferred to block 2, behind a wait for
+        // their detect inputs (= their epilogue 2b of block 23; normally long complete).  WN_WST = 6 keeps three blocks
+        // of weights ahead of the deferred load.
+        auto refill = [&](uint32_t m) {   // block m is finished everywhere: load block m + WN_WST into its stage
+          const uint32_t nl = m + WN_WST;
+          if (nl < total_loads && lane == 0) {
             mbar_arrive_expect_tx(&sm.wfull[nl % WN_WST], WN_WBLK);
             bulk_g2s(sm.W[nl % WN_WST], P.wblob + (size_t)(nl % 24) * WN_WBLK, WN_WBLK, &sm.wfull[nl % WN_WST]);
           }
+        };
+#ifdef WWB_WN_RS_DETECT
+        if (n_w >= 1 && k != 0) refill(n_w - 1);
+        if (k == 2 && n_u > 0) {
+#pragma unroll
+          for (int i = 0; i < WN_NT; ++i) WN_MBAR_WAIT(&sm.bar_dq[i], (n_u - 1) & 1, 9);
+          refill(n_w - 3);
         }
+#else
+        if (n_w >= 1) refill(n_w - 1);   // (k == 0: the detect loop below waited for every tile's block 23)
+#endif
       }
+#ifndef WWB_WN_RS_DETECT
       // detect head: D[128,32] = ReLU(skip)[128,32] * W1^T ; k-step 0 from the u columns, k-step 1 from the g columns
 #pragma unroll
       for (int i = 0; i < WN_NT; ++i) {
@@ -565,24 +617,30 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         }
         __syncwarp();
       }
+#endif
     }
   } else {
-    // =========================== res/skip-GEMM warp ===========================
+    // =========================== res/skip-GEMM warp (+ the detect GEMMs) ===========================
     // Tile after tile: when the tile's four warps have stored g (epilogue 1), issue its res and skip GEMMs
-    // (A = g from TMEM, + bias k-step).  Epilogue 2a of the tile will then overwrite rows that gate(k) of
-    // tile+1 reads, so that GEMM must have COMPLETED first (it is issued by another thread: no implicit order).
+    // (A = g from TMEM, + bias k-step).  The U rows are double-buffered by block parity, so epilogue 2a of (k, i) never
+    // overwrites rows that gate(k, i+1) still reads and this warp does not have to wait for that GEMM.
+    // The detect GEMMs of a group are issued from here too, each as soon as its tile has stored the detect input and
+    // WITHOUT holding up the next group's res/skip GEMMs (polled while this warp waits): the gate warp goes straight
+    // on to the next group, whose first blocks only involve tile 0 - issued in order behind gate(23, NT-1) by the gate warp,
+    // the detect GEMM of tile 0 and with it the next group's first gate GEMM waited ~3000 clk for the last tile's stagger.
     const int tile = 1, q = 0;   // (for the hang report)
     uint32_t n_gate = 0, n_rs = 0, n_u = 0, n_w = 0;
+    (void)tile; (void)q; (void)n_gate; (void)n_rs;
     const uint64_t dWr = make_desc(smem_u32(sm.W[0]) + WN_GATE_B, 768, 128);     // res/skip B: stage 0, hi plane
     const uint64_t dBr = make_desc(smem_u32(sm.W[0]) + WN_OFF_RBIAS, 768, 128);  // res/skip bias B: stage 0
+    const uint64_t dH = make_desc(smem_u32(sm.head.det1_B), 512, 128);           // detect B: k-step 0, hi plane
     const uint32_t ones = tmem + WN_C_ONE;
-    uint32_t cg[WN_NT];       // consumed phases of bar_g[i] = of bar_gate[i]: one per block the tile takes part in
+    uint32_t cg[WN_NT];       // consumed phases of bar_g[i]: one per block the tile takes part in
 #pragma unroll
     for (int i = 0; i < WN_NT; ++i) cg[i] = 0;
-    // This warp also owns the 48 padding rows in front of row 0 (x_pad of the NEXT block, see the header): it rewrites
-    // them right after issuing rs(k, 0) - gate(k, 0), their reader, has completed by then (epilogue 1 of tile 0 ran), and
-    // the next reader, gate(k+1, 0), waits for this warp's arrival on bar_u[0] - so the copy overlaps tile 0's res/skip
-    // GEMM and epilogue 2 instead of sitting inside it (it was ~350 clk of the ~2750-clk chain of a block).
+    // This warp also owns the padding rows in front of row 0 (x_pad of the NEXT block, see the header): it writes them
+    // (into the next level's buffer) right after issuing rs(k, 0); their reader, gate(k+1, 0), waits for this warp's
+    // arrival on bar_u[0] - so the copy overlaps tile 0's res/skip GEMM and epilogue 2 instead of sitting inside it.
     auto store_pad = [&](const unsigned char* chunk) {   // chunk: 64 bytes (hi0, hi1, lo0, lo1)
       const uint4* c4 = reinterpret_cast<const uint4*>(chunk);
       const uint4 c0 = c4[0], c1 = c4[1], c2 = c4[2], c3 = c4[3];
@@ -598,27 +656,80 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.bar_u[0]);
     };
+    // detect head of one tile: D[128,32] = ReLU(skip)[128,32] * W1^T ; k-step 0 from the u columns, k-step 1 from the g columns
+    int det_next = WN_NT;       // next tile of the pending group whose detect GEMM has not been issued (WN_NT: none pending)
+    uint32_t det_par = 0;       // bar_dq parity of the pending group
+    auto issue_detect = [&](int i) {
+      fence_after_sync();
+      if (elect_one()) {
+        const uint32_t tacc = tmem + (uint32_t)i * WN_TMEM_TILE;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint32_t ta = tacc + (kk == 0 ? WN_C_U : WN_C_G);
+          const uint64_t bh = dH + (uint64_t)((kk * 2 * 512) >> 4), bl = bh + (uint64_t)(2048 >> 4);
+          mma_f16_ts(tacc + WN_C_R, ta, bh, idesc_gate, kk != 0);
+          if (nsplit == 3) {
+            mma_f16_ts(tacc + WN_C_R, ta + 8, bh, idesc_gate, true);
+            mma_f16_ts(tacc + WN_C_R, ta, bl, idesc_gate, true);
+          }
+        }
+        mma_commit(&sm.bar_det[i]);
+      }
+      __syncwarp();
+    };
+    auto poll_detect = [&]() {   // warp-uniform
+#ifndef WWB_WN_RS_DETECT
+      return;
+#endif
+      if (det_next < WN_NT) {
+        const int ok = __shfl_sync(0xffffffffu, (int)mbar_test_wait(&sm.bar_dq[det_next], det_par), 0);
+        if (ok) { issue_detect(det_next); ++det_next; }
+      }
+    };
+    auto flush_detect = [&]() {
+      while (det_next < WN_NT) {
+        WN_MBAR_WAIT(&sm.bar_dq[det_next], det_par, 9);
+        issue_detect(det_next);
+        ++det_next;
+      }
+    };
     if ((int64_t)blockIdx.x < n_groups) store_pad(sm.head.pad0);   // level 0 of the first group
-    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++n_u) {
       for (int k = 0; k < 24; ++k, ++n_w) {
         const uint64_t wofs = (uint64_t)((n_w % WN_WST) * (WN_WBLK >> 4));
         const uint64_t bh = dWr + wofs, bb = dBr + wofs, lo_b = (uint64_t)(1536 >> 4);
         WN_MBAR_WAIT(&sm.wfull[n_w % WN_WST], (n_w / WN_WST) & 1, 11);   // (observe the weight load ourselves)
+#ifdef WWB_WN_RS_DETECT
+        if (k == 23) {
+          // From here on the tiles of THIS group deliver their detect inputs (tile 0 long before rs(23, NT-1) can be
+          // issued): served from the polls below and from those of the next group's first blocks.
+          flush_detect();          // (the previous group's: long complete)
+          det_next = 0;
+          det_par = n_u & 1;
+        }
+#endif
 #pragma unroll
         for (int i = 0; i < WN_NT; ++i) {
           if (k < P.join[i]) continue;
-          if (i == 3) WN_DBG(7, k, 0);
-          WN_MBAR_WAIT(&sm.bar_g[i], cg[i] & 1, 10);
+          if (i == 3) WN_DBG(WN_NT + 2, k, 0);
+          // busy-poll (this warp has nothing else to do and its wake-up latency is on every tile's chain), serving the
+          // previous group's detect GEMMs meanwhile
+#ifdef WWB_WN_RS_SHFL
+          while (!__shfl_sync(0xffffffffu, (int)mbar_test_wait(&sm.bar_g[i], cg[i] & 1), 0)) poll_detect();
+#else
+          while (det_next < WN_NT && !__shfl_sync(0xffffffffu, (int)mbar_test_wait(&sm.bar_g[i], cg[i] & 1), 0)) poll_detect();
+          mbar_spin(&sm.bar_g[i], cg[i] & 1);
+#endif
           // gate(k, i+1) reads rows of tile i that epilogue 2a of (k, i) overwrites.  cg[i+1] has not been advanced for
           // block k yet (tile i+1 comes next in this loop), so it is the phase of gate(k, i+1)
-          if (i < WN_NT - 1 && k >= P.join[i + 1]) WN_MBAR_WAIT(&sm.bar_gate[i + 1], cg[i + 1] & 1, 3);
+          if (i < WN_NT - 1 && k >= P.join[i + 1]) mbar_spin(&sm.bar_gate[i + 1], cg[i + 1] & 1);
           ++cg[i];
           if (i == 0 && lane == 0) WN_DBG2(k, 13);
-          if (i == 3) WN_DBG(7, k, 1);
+          if (i == 3) WN_DBG(WN_NT + 2, k, 1);
           fence_after_sync();
           if (elect_one()) {
-            // res (columns 32..47) and skip (48..79) in one N = 48 GEMM.  One commit: the next gate GEMM overwrites the
-            // g columns, so epilogue 2a must not release it before this GEMM has read them
+            // res and skip in one N = 48 GEMM.  One commit: the next gate GEMM overwrites the g columns, so epilogue 2a
+            // must not release it before this GEMM has read them
             const uint32_t tacc = tmem + i * WN_TMEM_TILE;
             mma_f16_ts(tacc + WN_C_R, tacc + WN_C_G, bh, idesc_rs, false);
             if (nsplit == 3) {
@@ -628,16 +739,17 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
             mma_f16_ts(tacc + WN_C_R, ones, bb, idesc_rs, true);
             mma_commit(&sm.bar_rs[i]);
             if (i == 0) WN_DBG2(k, 14);
-            if (i == 0) WN_DBG(5, k, 2);
-            if (i == WN_NT - 1) WN_DBG(5, k, 3);
+            if (i == 0) WN_DBG(WN_NT, k, 2);
+            if (i == WN_NT - 1) WN_DBG(WN_NT, k, 3);
           }
           __syncwarp();
           if (i == 0)    // padding rows of the next block (after block 23: level 0 of the next group)
             store_pad(k < 23 ? sm.W[n_w % WN_WST] + WN_OFF_F32 + 320 : sm.head.pad0);
-          if (i == 3) WN_DBG(7, k, 2);
+          if (i == 3) WN_DBG(WN_NT + 2, k, 2);
         }
       }
     }
+    flush_detect();
   }
   fence_before_sync();
   __syncthreads();
@@ -646,6 +758,9 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
 
 // the gate pre-activations are produced pre-scaled for ex2: tanh half by -2*log2(e), sigmoid half by -log2(e)
 static double gate_scale(int n) { return n < 16 ? -2.8853900817779268 : -1.4426950408889634; }
+// accumulator column of gate output n (0-15 tanh half, 16-31 sigmoid half): [tanh 0-7 | sigmoid 0-7 | tanh 8-15 | sigmoid 8-15],
+// so that epilogue 1 consumes the accumulator in two self-contained halves
+static int gate_col(int n) { const int c = n & 15; return (c >> 3) * 16 + (n >> 4) * 8 + (c & 7); }
 
 static void put_split(std::vector<unsigned char>& buf, size_t hi_off, size_t lo_off, float x, bool split) {
   __half h = __float2half_rn(x);
@@ -676,7 +791,7 @@ std::vector<unsigned char> wavenet_pack_blocks(const float* gate_w, const float*
     for (int k = 0; k < 48; ++k)
       for (int n = 0; n < 32; ++n) {
         const int c = k / 8, e = k % 8;
-        const size_t off = base + ((size_t)c * 32 + n) * 16 + e * 2;
+        const size_t off = base + ((size_t)c * 32 + gate_col(n)) * 16 + e * 2;
         put_split(out, off, off + 3072, (float)((double)gate_w[((size_t)b * 48 + k) * 32 + n] * (double)bn_mul[b * 16 + k % 16] * gate_scale(n)), true);
       }
     for (int k = 0; k < 16; ++k)
@@ -691,7 +806,7 @@ std::vector<unsigned char> wavenet_pack_blocks(const float* gate_w, const float*
     if (b < 23 && !put_pad_rows(out, base + WN_OFF_F32 + 320, bn_mul + (b + 1) * 16, bn_add + (b + 1) * 16)) return {};
     // bias operands of the 'ones' GEMM: row n = (hi, lo, 0, ...); the second k-chunk stays zero
     for (int n = 0; n < 32; ++n) {
-      const size_t off = base + WN_OFF_GBIAS + (size_t)n * 16;
+      const size_t off = base + WN_OFF_GBIAS + (size_t)gate_col(n) * 16;
       double bsum = gate_b[b * 32 + n];   // + W * bn_add (the folded BatchNorm shift)
       for (int k = 0; k < 48; ++k) bsum += (double)gate_w[((size_t)b * 48 + k) * 32 + n] * (double)bn_add[b * 16 + k % 16];
       put_split(out, off, off + 2, (float)(bsum * gate_scale(n)), true);
