@@ -1,4 +1,4 @@
-"""(needs a library built with NVCC_EXTRA=-DWWB_TIMELINE python -m wakeword_detection_b200.build --force) Timeline of the WaveNet kernel in shared-activation mode (sliding windows): period per block, per tile events."""
+"""(needs a library built with -DWWB_TIMELINE [-DWWB_WN_DBG2]: tools/build_variant.sh tl wavenet_tc.cu -DWWB_TIMELINE, run with WWB200_LIB=build/libwwb200_tl.so) Timeline of the WaveNet kernel in shared-activation mode (sliding windows): period per block, per tile events."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

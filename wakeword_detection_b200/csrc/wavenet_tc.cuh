@@ -8,41 +8,30 @@ namespace wwb {
 
 using namespace tc;
 
-#ifndef WWB_WN_G
-#define WWB_WN_G 4
-#define WWB_WN_NT 6
-#endif
-constexpr int WN_G = WWB_WN_G;                       // windows per group
-constexpr int WN_NT = WWB_WN_NT;                      // M tiles per group
-constexpr int WN_ROWS = WN_NT * 128;          // 640
-constexpr int WN_PAD = 16 * WN_G;                    // leading padding rows of the U buffer: 2 * max dilation (8) * WN_G
+constexpr int WN_G = 4;                       // windows per group
+constexpr int WN_NT = 6;                      // M tiles per group (4 x 182 = 728 of 768 rows)
+constexpr int WN_ROWS = WN_NT * 128;          // 768
+constexpr int WN_PAD = 16 * WN_G;             // leading padding rows of the U buffer: 2 * max dilation (8) * WN_G
 constexpr int WN_UROWS = WN_ROWS + WN_PAD;
-constexpr int WN_MAXT = 182;                  // WN_G * 182 = 546 rows <= WN_ROWS
+constexpr int WN_MAXT = 182;                  // WN_G * 182 = 728 rows <= WN_ROWS
 constexpr int WN_CHUNK_WARM = 180;            // stream mode: rows of a chunk inside some receptive field (D(23) = 180)
 constexpr int WN_CHUNK_STEP = WN_ROWS - WN_CHUNK_WARM;
 constexpr int WN_SNAP_F = 48;                 // floats per snapshot row: x[16], skip prefix sum[32]
 constexpr int WN_PU = WN_UROWS * 16;          // bytes per U chunk panel
 constexpr int WN_UBUF = 4 * WN_PU;            // one U buffer: hi and lo planes of two k-chunks
-constexpr int WN_EPI_WARPS = WN_NT * 4;       // 20
+constexpr int WN_EPI_WARPS = WN_NT * 4;       // 24
 constexpr int WN_EPI_THREADS = WN_EPI_WARPS * 32;
-constexpr int WN_THREADS = (WN_EPI_WARPS + 2) * 32;   // + the gate-GEMM / loader warp + the res/skip-GEMM warp = 704
+constexpr int WN_THREADS = (WN_EPI_WARPS + 2) * 32;   // + the gate-GEMM / loader warp + the res/skip-GEMM warp = 832
 constexpr int WN_GATE_B = 6144, WN_RS_B = 3072;   // gate / res+skip B operands (hi and lo planes)
 constexpr int WN_F32_B = 512;                     // misc: bytes [320, 384) = the NEXT block's padding rows (hi0, hi1, lo0, lo1)
 constexpr int WN_GBIAS_B = 1024, WN_RBIAS_B = 1536;   // bias B operands for the 'ones' GEMM (k0 = hi, k1 = lo)
 constexpr int WN_OFF_F32 = WN_GATE_B + WN_RS_B, WN_OFF_GBIAS = WN_OFF_F32 + WN_F32_B, WN_OFF_RBIAS = WN_OFF_GBIAS + WN_GBIAS_B;
 constexpr int WN_WBLK = WN_OFF_RBIAS + WN_RBIAS_B;    // 12288 bytes of one block's weight blob
 constexpr int WN_WST = 5;                     // weight ring stages
-#ifdef WWB_WN_TILE96
-constexpr int WN_TMEM_TILE = 96;
-constexpr int WN_C_G = 0;
-constexpr int WN_C_R = 32;
-constexpr int WN_C_U = 80;
-#else
 constexpr int WN_TMEM_TILE = 80;              // TMEM columns per tile:
 constexpr int WN_C_G = 0;                     //   0..31  gate accumulator; g hi/lo (A of res/skip) overwrites 0..15 once epilogue 1 has read it
 constexpr int WN_C_R = 16;                    //   16..31 res accumulator (over the consumed sigmoid half of the gate accumulator), 32..63 skip accumulator (detect: 16..47)
 constexpr int WN_C_U = 64;                    //   64..79 u hi/lo (A of the gate's unshifted tap)
-#endif
 constexpr int WN_DBG_ROLES = WN_NT + 3;          // timeline roles: tiles 0..NT-1, issuing warps, group boundary, res/skip warp
 constexpr int WN_C_ONE = WN_NT * WN_TMEM_TILE;   // 480..487: constant A chunk (k0 = k1 = 1, rest 0), shared by all tiles: adds the biases
 
@@ -88,25 +77,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-// 2^x for a pair on the FMA pipe (A/B switch WWB_WN_EX2_POLY: the SFU does 4 lanes per clock and scheduler and epilogue 1 is
-// bound by its 40 MUFU operations per row): round-to-nearest split x = n + f with the 1.5 * 2^23 trick, 2^f by a degree-5
-// interpolant on [-0.5, 0.5] (2.2e-7 relative, like ex2.approx), 2^n added into the exponent field.  x in [-125, 30].
-__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& r0, float& r1) {
-  const u64 xx = pk(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
-  const u64 magic = pk(12582912.f, 12582912.f);
-  const u64 t = fadd2(xx, magic);
-  const u64 f = fsub2(xx, fsub2(t, magic));
-  u64 p = ffma2(pk(0.0013390863314270973f, 0.0013390863314270973f), f, pk(0.009676031768321991f, 0.009676031768321991f));
-  p = ffma2(p, f, pk(0.055503569543361664f, 0.055503569543361664f));
-  p = ffma2(p, f, pk(0.2402210682630539f, 0.2402210682630539f));
-  p = ffma2(p, f, pk(0.6931471824645996f, 0.6931471824645996f));
-  p = ffma2(p, f, pk(1.0000001192092896f, 1.0000001192092896f));
-  float p0, p1, t0, t1;
-  upk(p, p0, p1);
-  upk(t, t0, t1);
-  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
