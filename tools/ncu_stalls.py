@@ -1,15 +1,18 @@
-"""Per-kernel stall summary from an .ncu-rep (source page):  python tools/ncu_stalls.py rep [kernel-substr] [topN]"""
+"""Per-kernel stall summary from an .ncu-rep (source page):  python tools/ncu_stalls.py rep [kernel-substr] [topN] [occurrence]
+(occurrence: which launch of that kernel in the report, default 0)"""
 import csv, subprocess, sys, io, collections, re
-rep = sys.argv[1]; want = sys.argv[2] if len(sys.argv) > 2 else ""; topn = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+rep = sys.argv[1]; want = sys.argv[2] if len(sys.argv) > 2 else ""; topn = int(sys.argv[3]) if len(sys.argv) > 3 else 25; occ = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 blocks = re.split(r'(?m)^"Kernel Name",', out)
-seen = set()
+seen = collections.Counter()
 for blk in blocks[1:]:
     lines = blk.split("\n")
     name = lines[0].strip().strip('",')
-    if want not in name or name in seen:
+    if want not in name:
         continue
-    seen.add(name)
+    seen[name] += 1
+    if seen[name] - 1 != occ:
+        continue
     rows = list(csv.reader(io.StringIO("\n".join(lines[1:]))))
     h = rows[0]; idx = {k: i for i, k in enumerate(h)}; data = [r for r in rows[1:] if len(r) == len(h)]
     def f(r, k):

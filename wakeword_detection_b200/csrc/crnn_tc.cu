@@ -622,9 +622,26 @@ __device__ __forceinline__ float rcpf(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float sigmoid_fast(float v) { return rcpf(1.f + ex2f(-1.4426950408889634f * v)); }
-// tanh(v) = 1 - 2/(1 + e^(2v)); e^(2v) = inf gives exactly 1, 0 gives exactly -1
-__device__ __forceinline__ float tanh_fast(float v) { return fmaf(-2.f, rcpf(1.f + ex2f(2.8853900817779268f * v)), 1.f); }
+
+// GRU gates of TWO units with 8 SFU operations instead of 12 (the recurrence kernels are bound by the SFU: 4 lanes per
+// clock and scheduler): one reciprocal serves a pair of denominators, 1/d0 = d1 * rcp(d0 d1).  z and r of a unit share
+// one, the candidates of the two units the other.  The exponents are clamped at 60 (2^120 stays finite in the
+// products; sigmoid is 9e-19 and tanh 1 to 2e-18 there).  az / ar = pre-activations of z / r, hb = U_h h + b_h, xh = the
+// candidate's input part; h is updated in place: h' = z h + (1 - z) c.
+__device__ __forceinline__ void gru_gates2(float az0, float ar0, float hb0, float xh0, float az1, float ar1, float hb1, float xh1,
+                                           float& h0, float& h1) {
+  const float L2E = 1.4426950408889634f;
+  const float dz0 = 1.f + ex2f(fminf(-L2E * az0, 60.f)), dr0 = 1.f + ex2f(fminf(-L2E * ar0, 60.f));
+  const float dz1 = 1.f + ex2f(fminf(-L2E * az1, 60.f)), dr1 = 1.f + ex2f(fminf(-L2E * ar1, 60.f));
+  const float p0 = rcpf(dz0 * dr0), p1 = rcpf(dz1 * dr1);
+  const float z0 = dr0 * p0, r0 = dz0 * p0, z1 = dr1 * p1, r1 = dz1 * p1;
+  const float dc0 = 1.f + ex2f(fminf(2.f * L2E * fmaf(r0, hb0, xh0), 60.f));
+  const float dc1 = 1.f + ex2f(fminf(2.f * L2E * fmaf(r1, hb1, xh1), 60.f));
+  const float pc = rcpf(dc0 * dc1);
+  const float c0 = fmaf(-2.f, dc1 * pc, 1.f), c1 = fmaf(-2.f, dc0 * pc, 1.f);   // tanh(v) = 1 - 2 / (1 + e^(2v))
+  h0 = fmaf(z0, h0 - c0, c0);
+  h1 = fmaf(z1, h1 - c1, c1);
+}
 
 __device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
@@ -719,15 +736,12 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
             for (int i = 0; i < CW; ++i) { hz[i] = 0.f; hr[i] = 0.f; hh[i] = 0.f; }
           }
 #pragma unroll
-          for (int i = 0; i < CW; ++i) {
+          for (int i = 0; i < CW; i += 2) {
             const float4 vz = xc[0][i >> 2], vr = xc[1][i >> 2], vh = xc[2][i >> 2];
-            const float xz = (i & 3) == 0 ? vz.x : (i & 3) == 1 ? vz.y : (i & 3) == 2 ? vz.z : vz.w;
-            const float xr = (i & 3) == 0 ? vr.x : (i & 3) == 1 ? vr.y : (i & 3) == 2 ? vr.z : vr.w;
-            const float xh = (i & 3) == 0 ? vh.x : (i & 3) == 1 ? vh.y : (i & 3) == 2 ? vh.z : vh.w;
-            const float z = sigmoid_fast(xz + hz[i]);
-            const float rr = sigmoid_fast(xr + hr[i]);
-            const float c = tanh_fast(fmaf(rr, hh[i] + bh[u * CW + i], xh));
-            h[u * CW + i] = fmaf(z, h[u * CW + i] - c, c);
+            const bool lo = (i & 3) == 0;
+            gru_gates2((lo ? vz.x : vz.z) + hz[i], (lo ? vr.x : vr.z) + hr[i], hh[i] + bh[u * CW + i], lo ? vh.x : vh.z,
+                       (lo ? vz.y : vz.w) + hz[i + 1], (lo ? vr.y : vr.w) + hr[i + 1], hh[i + 1] + bh[u * CW + i + 1], lo ? vh.y : vh.w,
+                       h[u * CW + i], h[u * CW + i + 1]);
           }
         }
         // hand the stage back once every lane's loads from it have completed (the arrive depends on the last loaded
@@ -1011,12 +1025,9 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru2_fused_tc_kernel(const G2Pa
             if (lane == 0) mbar_arrive(&sm.acc_free[d]);
           }
 #pragma unroll
-          for (int i = 0; i < CW; ++i) {
-            const float z = sigmoid_fast(az[i]);
-            const float rr = sigmoid_fast(ar[i]);
-            const float c = tanh_fast(fmaf(rr, hh[i] + bh[u * CW + i], xh[i]));
-            h[u * CW + i] = fmaf(z, h[u * CW + i] - c, c);
-          }
+          for (int i = 0; i < CW; i += 2)
+            gru_gates2(az[i], ar[i], hh[i] + bh[u * CW + i], xh[i], az[i + 1], ar[i + 1], hh[i + 1] + bh[u * CW + i + 1], xh[i + 1],
+                       h[u * CW + i], h[u * CW + i + 1]);
         }
         if (s < GR_T - 1) {
           uint32_t hr16[16], lr16[16];

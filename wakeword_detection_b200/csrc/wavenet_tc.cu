@@ -127,7 +127,8 @@ __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
   while (!mbar_test_wait(bar, parity)) { }
 }
 // A/B switch (tools/build_variant.sh): -DWWB_WN_ISS_SUSPEND puts the two issuing warps back on the suspending try_wait
-// (busy-polling them: 13.85 -> 13.39 ms per 512 x 10 s; busy-polling the epilogue warps too: 15.5 ms)
+// (busy-polling them: 13.85 -> 13.39 ms per 512 x 10 s; busy-polling the epilogue warps too: 15.5 ms, and 13.7-14.1 ms when only
+// their res/skip wait or only the blocks with few active tiles poll)
 #define WN_WAIT_E(bar, par, id) WN_MBAR_WAIT(bar, par, id)
 #ifndef WWB_WN_ISS_SUSPEND
 #define WN_WAIT_I(bar, par, id) WN_SPIN(bar, par, id)
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
 #endif
     unsigned char* const Urow = sm.U + (WN_PAD + o) * 16;
     float4* const sk = sm.skip + o;           // this row's skip sums: sk[c4 * WN_ROWS], conflict-free 16-byte accesses
+    // (keeping 8 / 16 / 24 / 32 of the 32 sums in registers instead: 14.15 / 14.28 / 13.93 / 13.96 ms against 13.50 - profiles/r2_notes.md)
     {
       uint32_t one[16];
 #pragma unroll
