@@ -142,13 +142,13 @@ def cpu_reference_rate(models, n_streams, seconds_per_stream, processes):
 
 
 def measured_traffic(kernel, S, N):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (taken at 512 streams; the
-    traffic is per stream, so it is scaled to the step's stream count)
-    (profiles/r1_traffic.json); only valid for the shape it was captured on."""
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r2_traffic.json, taken at 512 streams x 10 s; the traffic - per-frame snapshots and input-layer rows - is
+    per stream, so it is scaled to the step's stream count); only valid for the stream length it was captured on."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(kernel)
-        if d and d["streams"] == S and abs(d["seconds"] - N / 16000.0) < 1e-9:
-            return int(d["bytes_per_launch"])
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get(kernel)
+        if d and abs(d["seconds"] - N / 16000.0) < 1e-9 and (d["streams"] == S or d.get("scales_with") == "streams"):
+            return int(round(d["bytes_per_launch"] * (S / float(d["streams"]))))
     except Exception:
         pass
     return None
@@ -653,7 +653,7 @@ def main():
         tile_blocks = sum(24 - int(np.argmax(D > (128 * i) // G)) for i in range(NT))          # 76
         frac = (tile_blocks * 128.0 / G + (F / (NT * 128.0 - 180.0)) * NT * 24 * 128.0 / nwin["Wavenet"]) / (L_wn * 24.0)
         exe = FLOP_PER_WINDOW["Wavenet"] * frac
-        extra["Wavenet_shared_activations"] = {"executed_fraction_of_tile_blocks": frac,
+        extra["Wavenet_shared_activations"] = {"executed_fraction_of_row_blocks": frac,
                                                "executed_TFLOPs": S * nwin["Wavenet"] * exe / (per["Wavenet"] / 1e3) / 1e12}
 
     if rank == 0 and models and not args.no_extras:
