@@ -233,7 +233,7 @@ def test_crnn_tc_many_tiles_matches_f32_path():
 
 
 def test_wavenet_tc_many_groups_matches_f32_path():
-    """4097 windows (1366 groups of 3, ragged last group, > 9 groups per SM) through both paths,
+    """4097 windows (1025 groups of 4, ragged last group, > 6 groups per SM) through both paths,
     sliding hop-1 windows of real filter output; also the encoder output tensor."""
     e32, etc = get_engine("Wavenet", "f32"), get_engine("Wavenet", "tc")
     pcm = synth.device_pcm(17, 160 * 421 + 512, seed=5, device=e32.device)
@@ -247,6 +247,20 @@ def test_wavenet_tc_many_groups_matches_f32_path():
     assert float((ea - eb).abs().max()) < 5e-4 * max(1.0, float(ea.abs().max()))
     da, db = e32.detect(ea), etc.detect(eb)
     assert float((da - db).abs().max()) < 2e-4
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 6, 7, 9])
+def test_wavenet_ragged_groups_vs_oracle(n):
+    """Fewer windows than a group of 4 holds, and every remainder of the last group: the rows of the missing windows are
+    masked, the posteriors of the present ones equal the oracle's and do not depend on what else is in the batch."""
+    w = load_weights("Wavenet")
+    eng = get_engine("Wavenet", "tc")
+    X = _windows("wavenet", w)[:9]
+    post = eng.posteriors(X[:n], hop=1).cpu().numpy()[:, 0]
+    assert post.shape == (n,)
+    assert np.abs(post - R.posterior(X[:n], w)).max() < POST_ATOL
+    full = eng.posteriors(X, hop=1).cpu().numpy()[:, 0]
+    assert np.array_equal(post, full[:n])
 
 
 def test_known_answers_on_device():

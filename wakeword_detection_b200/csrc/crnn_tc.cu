@@ -579,7 +579,14 @@ using namespace tc;
 constexpr int GR_T = 19;
 constexpr int GR_H_BYTES = 2 * 4 * 128 * 16;     // hi + lo planes, K = 32
 constexpr int GR_U_BYTES = 2 * 4 * 96 * 16;
-constexpr int GR_THREADS = 9 * 32;
+constexpr int GR_EPI_WARPS = 16;                 // 2 directions x 4 lane quadrants x 2 unit halves: TWO threads per (window, direction),
+                                                 // units 0-15 and 16-31 (a warp reaches the tensor-memory lanes 32 (warp % 4) ..., so warps w and
+                                                 // w + 8 share a quadrant): 96 instead of 168 registers per thread, four epilogue warps per
+                                                 // scheduler instead of two.  Measured neutral (CRNN stage 2.70 -> 2.68 ms per 512 x 10 s): the
+                                                 // recurrences are not bound by per-warp latency but by the operand traffic of a step
+                                                 // (layer 1: 96 KB of xw slabs per CTA and step from L2 = 3.2 TB/s over the launch; layer 2: 2 GB of
+                                                 // layer-1 output read back from HBM per 512 x 10 s)
+constexpr int GR_THREADS = (GR_EPI_WARPS + 1) * 32;   // + the MMA issuer / loader warp = 544
 
 constexpr int G2_A_BYTES = 2 * 8 * 128 * 16;       // layer-1 output of 128 windows at one step as a packed fp16 hi/lo operand (K = 64): 32 KB
 constexpr int GR_X_BYTES = 24 * 128 * 16;          // one direction's xw of one step: 24 float4 columns x 128 windows (contiguous in HBM)
@@ -654,14 +661,16 @@ __device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
 
 __device__ __forceinline__ void tmem_ldN(uint32_t taddr, float (&v)[8]) { tmem_ld8f(taddr, v); }
 __device__ __forceinline__ void tmem_ldN(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 // A/B switch (tools/build_variant.sh): the recurrence kernels' issuing warp busy-polls the barriers on the per-step chain
 #ifdef WWB_GR_ISS_SPIN
 #define GR_ISS_WAIT(bar, par) do { while (!mbar_test_wait(bar, par)) { } } while (0)
 #else
 #define GR_ISS_WAIT(bar, par) mbar_wait(bar, par)
-#endif
-#ifndef GR_CHUNKS
-#define GR_CHUNKS 2                                // the epilogue processes the 32 units in this many pieces (2: 2.94 -> 2.90 ms CRNN stage against 4)
 #endif
 
 __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParams P) {
@@ -678,38 +687,39 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
   if (tid < 64) (&sm.bh[0][0])[tid] = P.bh[tid];
   if (tid == 0) {
     for (int d = 0; d < 2; ++d) {
-      mbar_init(&sm.acc_full[d], 1); mbar_init(&sm.h_ready[d], 4);
-      for (int i = 0; i < GR_XST; ++i) { mbar_init(&sm.x_full[d][i], 1); mbar_init(&sm.x_empty[d][i], 4); }
+      mbar_init(&sm.acc_full[d], 1); mbar_init(&sm.h_ready[d], 8);
+      for (int i = 0; i < GR_XST; ++i) { mbar_init(&sm.x_full[d][i], 1); mbar_init(&sm.x_empty[d][i], 8); }
     }
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(&sm.tmem_base, 256);
+  if (warp == GR_EPI_WARPS) tmem_alloc(&sm.tmem_base, 256);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp < 8) {
-    const int d = warp >> 2, q = warp & 3;
+  if (warp < GR_EPI_WARPS) {
+    const int d = (warp >> 2) & 1, q = warp & 3, half = warp >> 3;
     const int r = q * 32 + lane;
-    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + d * 96;
-    const uint32_t th = tmem + ((uint32_t)(q * 32) << 16) + 192 + d * 32;   // this row's h: hi 16 columns, lo 16 columns
-    const float* bh = sm.bh[d];
+    const int ub = half * 16;                         // this thread's units: ub .. ub + 15
+    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + d * 96 + ub;
+    const uint32_t th = tmem + ((uint32_t)(q * 32) << 16) + 192 + d * 32 + half * 8;   // this row's h: hi 16 columns, lo 16 columns (2 units per column)
+    const float* bh = sm.bh[d] + ub;
     uint32_t n_acc = 0, n_x = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t b = tile * 128 + r;
       const bool valid = b < n_win;
-      float h[32];
+      float h[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) h[i] = 0.f;
+      for (int i = 0; i < 16; ++i) h[i] = 0.f;
       for (int s = 0; s < GR_T; ++s, ++n_x) {
         const int t = d ? GR_T - 1 - s : s;
         // this direction's xw slab of the step was fetched by the TMA engine one step ahead (per-thread loads could
         // prefetch only one 400-clock chunk ahead of ~1500 clocks of DRAM latency)
         const int xs = n_x % GR_XST;
         mbar_wait(&sm.x_full[d][xs], (n_x / GR_XST) & 1);
-        const float4* xp = reinterpret_cast<const float4*>(sm.x[d][xs]) + r;
+        const float4* xp = reinterpret_cast<const float4*>(sm.x[d][xs]) + r + (ub / 4) * 128;
         float x_last = 0.f;
         if (s > 0) {
           mbar_wait(&sm.acc_full[d], n_acc & 1);
@@ -717,31 +727,30 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
           fence_after_sync();
         }
 #pragma unroll
-        for (int u = 0; u < GR_CHUNKS; ++u) {
-          constexpr int CW = 32 / GR_CHUNKS, C4 = CW / 4;   // units / float4 columns per chunk and gate
-          float4 xc[3][C4];
+        for (int u = 0; u < 2; ++u) {                 // two pieces of 8 units
+          float4 xc[3][2];
 #pragma unroll
           for (int g = 0; g < 3; ++g)
 #pragma unroll
-            for (int i = 0; i < C4; ++i) xc[g][i] = xp[(g * 8 + u * C4 + i) * 128];
-          if (u == GR_CHUNKS - 1) x_last = xc[2][C4 - 1].w;
-          float hz[CW], hr[CW], hh[CW];
+            for (int i = 0; i < 2; ++i) xc[g][i] = xp[(g * 8 + u * 2 + i) * 128];
+          if (u == 1) x_last = xc[2][1].w;
+          float hz[8], hr[8], hh[8];
           if (s > 0) {
-            tmem_ldN(tbase + u * CW, hz);
-            tmem_ldN(tbase + 32 + u * CW, hr);
-            tmem_ldN(tbase + 64 + u * CW, hh);
+            tmem_ld8f(tbase + u * 8, hz);
+            tmem_ld8f(tbase + 32 + u * 8, hr);
+            tmem_ld8f(tbase + 64 + u * 8, hh);
             tmem_ld_wait();
           } else {
 #pragma unroll
-            for (int i = 0; i < CW; ++i) { hz[i] = 0.f; hr[i] = 0.f; hh[i] = 0.f; }
+            for (int i = 0; i < 8; ++i) { hz[i] = 0.f; hr[i] = 0.f; hh[i] = 0.f; }
           }
 #pragma unroll
-          for (int i = 0; i < CW; i += 2) {
+          for (int i = 0; i < 8; i += 2) {
             const float4 vz = xc[0][i >> 2], vr = xc[1][i >> 2], vh = xc[2][i >> 2];
             const bool lo = (i & 3) == 0;
-            gru_gates2((lo ? vz.x : vz.z) + hz[i], (lo ? vr.x : vr.z) + hr[i], hh[i] + bh[u * CW + i], lo ? vh.x : vh.z,
-                       (lo ? vz.y : vz.w) + hz[i + 1], (lo ? vr.y : vr.w) + hr[i + 1], hh[i + 1] + bh[u * CW + i + 1], lo ? vh.y : vh.w,
-                       h[u * CW + i], h[u * CW + i + 1]);
+            gru_gates2((lo ? vz.x : vz.z) + hz[i], (lo ? vr.x : vr.z) + hr[i], hh[i] + bh[u * 8 + i], lo ? vh.x : vh.z,
+                       (lo ? vz.y : vz.w) + hz[i + 1], (lo ? vr.y : vr.w) + hr[i + 1], hh[i + 1] + bh[u * 8 + i + 1], lo ? vh.y : vh.w,
+                       h[u * 8 + i], h[u * 8 + i + 1]);
           }
         }
         // hand the stage back once every lane's loads from it have completed (the arrive depends on the last loaded
@@ -752,36 +761,36 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
           tok = __reduce_or_sync(0xffffffffu, tok);
           if (lane == 0) mbar_arrive_after(&sm.x_empty[d][xs], tok);
         }
-        uint32_t hr16[16], lr16[16];
+        uint32_t hr8[8], lr8[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) split_pair(h[2 * c], h[2 * c + 1], hr16[c], lr16[c]);
+        for (int c = 0; c < 8; ++c) split_pair(h[2 * c], h[2 * c + 1], hr8[c], lr8[c]);
         if (s < GR_T - 1) {
           fence_before_sync();
-          tmem_st16(th, hr16);
-          tmem_st16(th + 16, lr16);
+          tmem_st8(th, hr8);
+          tmem_st8(th + 16, lr8);
           tmem_st_wait();
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.h_ready[d]);
         }
         if (valid && P.seq_out) {
-          float4* dst = reinterpret_cast<float4*>(P.seq_out + (b * GR_T + t) * 64 + d * 32);
+          float4* dst = reinterpret_cast<float4*>(P.seq_out + (b * GR_T + t) * 64 + d * 32 + ub);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
         }
         if (valid && P.seq_packed) {   // the split computed for the recurrent GEMM is the next layer's A operand: 512 contiguous bytes per warp store
-          unsigned char* dst = P.seq_packed + ((size_t)((b >> 7) * GR_T + t) * G2_A_BYTES) + (size_t)((d * 4) * 128 + (int)(b & 127)) * 16;
+          unsigned char* dst = P.seq_packed + ((size_t)((b >> 7) * GR_T + t) * G2_A_BYTES) + (size_t)((d * 4 + half * 2) * 128 + (int)(b & 127)) * 16;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            *reinterpret_cast<uint4*>(dst + u * 2048) = make_uint4(hr16[4 * u], hr16[4 * u + 1], hr16[4 * u + 2], hr16[4 * u + 3]);
-            *reinterpret_cast<uint4*>(dst + G2_A_BYTES / 2 + u * 2048) = make_uint4(lr16[4 * u], lr16[4 * u + 1], lr16[4 * u + 2], lr16[4 * u + 3]);
+          for (int u = 0; u < 2; ++u) {
+            *reinterpret_cast<uint4*>(dst + u * 2048) = make_uint4(hr8[4 * u], hr8[4 * u + 1], hr8[4 * u + 2], hr8[4 * u + 3]);
+            *reinterpret_cast<uint4*>(dst + G2_A_BYTES / 2 + u * 2048) = make_uint4(lr8[4 * u], lr8[4 * u + 1], lr8[4 * u + 2], lr8[4 * u + 3]);
           }
         }
       }
       if (valid && P.last_out) {
-        float4* dst = reinterpret_cast<float4*>(P.last_out + b * 64 + d * 32);
+        float4* dst = reinterpret_cast<float4*>(P.last_out + b * 64 + d * 32 + ub);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
       }
     }
   } else {
@@ -858,7 +867,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 256);
+  if (warp == GR_EPI_WARPS) tmem_dealloc(tmem, 256);
 }
 
 // U [96][32] (gate-major rows z|r|h) -> [plane][4 chunks][96][8 halves]
@@ -916,9 +925,6 @@ int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* 
 constexpr int G2_W_BYTES = 2 * 8 * 96 * 16;        // per direction: hi + lo planes, K = 64, N = 96
 constexpr int G2_BIAS_BYTES = 2 * 96 * 16;         // B operand of the 'ones' k-step
 constexpr int G2_AST = 2;                          // A slab stages per direction
-#ifndef G2_CHUNKS
-#define G2_CHUNKS 2                                // the epilogue reads the accumulator in this many pieces (2: 2.97 -> 2.92 ms CRNN stage against 4)
-#endif
 
 struct G2Smem {
   unsigned char a[2][G2_AST][G2_A_BYTES];
@@ -965,12 +971,12 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru2_fused_tc_kernel(const G2Pa
   }
   if (tid == 0) {
     for (int d = 0; d < 2; ++d) {
-      mbar_init(&sm.acc_full[d], 1); mbar_init(&sm.acc_free[d], 4); mbar_init(&sm.h_ready[d], 4);
+      mbar_init(&sm.acc_full[d], 1); mbar_init(&sm.acc_free[d], 8); mbar_init(&sm.h_ready[d], 8);
       for (int i = 0; i < G2_AST; ++i) { mbar_init(&sm.a_full[d][i], 1); mbar_init(&sm.a_empty[d][i], 1); }
     }
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(&sm.tmem_base, 512);
+  if (warp == GR_EPI_WARPS) tmem_alloc(&sm.tmem_base, 512);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -989,53 +995,53 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru2_fused_tc_kernel(const G2Pa
   __syncthreads();
   fence_after_sync();
 
-  if (warp < 8) {
-    const int d = warp >> 2, q = warp & 3;
+  if (warp < GR_EPI_WARPS) {
+    const int d = (warp >> 2) & 1, q = warp & 3, half = warp >> 3;
     const int r = q * 32 + lane;
-    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + d * 128;
-    const uint32_t th = tmem + ((uint32_t)(q * 32) << 16) + TM_H + d * 32;
-    const float* bh = sm.bh[d];
+    const int ub = half * 16;                         // this thread's units: ub .. ub + 15
+    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + d * 128 + ub;
+    const uint32_t th = tmem + ((uint32_t)(q * 32) << 16) + TM_H + d * 32 + half * 8;
+    const float* bh = sm.bh[d] + ub;
     uint32_t n_acc = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t b = tile * 128 + r;
       const bool valid = b < n_win;
-      float h[32];
+      float h[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) h[i] = 0.f;
+      for (int i = 0; i < 16; ++i) h[i] = 0.f;
       for (int s = 0; s < GR_T; ++s, ++n_acc) {
         mbar_wait(&sm.acc_full[d], n_acc & 1);
         fence_after_sync();
 #pragma unroll
-        for (int u = 0; u < G2_CHUNKS; ++u) {
-          constexpr int CW = 32 / G2_CHUNKS;   // units per chunk
-          float xh[CW], az[CW], ar[CW], hh[CW];
-          tmem_ldN(tbase + u * CW, xh);
-          tmem_ldN(tbase + 32 + u * CW, az);
-          tmem_ldN(tbase + 64 + u * CW, ar);
+        for (int u = 0; u < 2; ++u) {                 // two pieces of 8 units
+          float xh[8], az[8], ar[8], hh[8];
+          tmem_ld8f(tbase + u * 8, xh);
+          tmem_ld8f(tbase + 32 + u * 8, az);
+          tmem_ld8f(tbase + 64 + u * 8, ar);
           if (s > 0) {
-            tmem_ldN(tbase + 96 + u * CW, hh);
+            tmem_ld8f(tbase + 96 + u * 8, hh);
           } else {
 #pragma unroll
-            for (int i = 0; i < CW; ++i) hh[i] = 0.f;
+            for (int i = 0; i < 8; ++i) hh[i] = 0.f;
           }
           tmem_ld_wait();
-          if (u == G2_CHUNKS - 1) {   // the accumulator has been read: the next step's input projection may overwrite it
+          if (u == 1) {   // the accumulator has been read: the next step's input projection may overwrite it
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.acc_free[d]);
           }
 #pragma unroll
-          for (int i = 0; i < CW; i += 2)
-            gru_gates2(az[i], ar[i], hh[i] + bh[u * CW + i], xh[i], az[i + 1], ar[i + 1], hh[i + 1] + bh[u * CW + i + 1], xh[i + 1],
-                       h[u * CW + i], h[u * CW + i + 1]);
+          for (int i = 0; i < 8; i += 2)
+            gru_gates2(az[i], ar[i], hh[i] + bh[u * 8 + i], xh[i], az[i + 1], ar[i + 1], hh[i + 1] + bh[u * 8 + i + 1], xh[i + 1],
+                       h[u * 8 + i], h[u * 8 + i + 1]);
         }
         if (s < GR_T - 1) {
-          uint32_t hr16[16], lr16[16];
+          uint32_t hr8[8], lr8[8];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) split_pair(h[2 * c], h[2 * c + 1], hr16[c], lr16[c]);
+          for (int c = 0; c < 8; ++c) split_pair(h[2 * c], h[2 * c + 1], hr8[c], lr8[c]);
           fence_before_sync();
-          tmem_st16(th, hr16);
-          tmem_st16(th + 16, lr16);
+          tmem_st8(th, hr8);
+          tmem_st8(th + 16, lr8);
           tmem_st_wait();
           fence_before_sync();
           __syncwarp();
@@ -1043,9 +1049,9 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru2_fused_tc_kernel(const G2Pa
         }
       }
       if (valid) {
-        float4* dst = reinterpret_cast<float4*>(P.last_out + b * 64 + d * 32);
+        float4* dst = reinterpret_cast<float4*>(P.last_out + b * 64 + d * 32 + ub);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
       }
     }
   } else {
@@ -1136,7 +1142,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru2_fused_tc_kernel(const G2Pa
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == GR_EPI_WARPS) tmem_dealloc(tmem, 512);
 }
 
 // W2 [192][64] (row = fwd gates z|r|h then bwd gates z|r|h) -> per direction [plane][8 chunks][96 rows xh|z|r][8 halves]
