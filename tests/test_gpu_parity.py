@@ -895,7 +895,9 @@ def test_encoders_are_deterministic(wname):
 
 
 @pytest.mark.parametrize("S,F,hop", [(2, 411, 2), (5, 998, 2), (2, 700, 1), (3, 600, 4), (2, 1200, 8), (1, 153, 2), (40, 998, 2),
-                                     (2, 1015, 2), (2, 1015, 1), (2, 1021, 2), (3, 151 + 2 * 72, 2)])   # 1015: column t = 18 of the last windows is the strip's last row
+                                     (2, 1015, 2), (2, 1015, 1), (2, 1021, 2), (3, 151 + 2 * 72, 2),   # 1015: column t = 18 of the last windows is the strip's last row
+                                     (4, 389, 2), (4, 391, 2), (5, 393, 2), (5, 395, 2), (3, 403, 2)])   # 120..127 windows per stream: position-ring tiles
+                                                                                                          # that start 0..3 windows before a stream's end
 def test_crnn_shared_columns_bit_identical_to_per_window_path(S, F, hop):
     """Sliding-window batches compute every conv / GRU-1 projection column once per stream position (crnn_tc.cu,
     CrnnShare); WWB_CRNN_NO_SHARE=1 forces the per-window tiles.  Same MMAs on the same operands: identical bits."""

@@ -591,6 +591,8 @@ constexpr int GR_THREADS = (GR_EPI_WARPS + 1) * 32;   // + the MMA issuer / load
 constexpr int G2_A_BYTES = 2 * 8 * 128 * 16;       // layer-1 output of 128 windows at one step as a packed fp16 hi/lo operand (K = 64): 32 KB
 constexpr int GR_X_BYTES = 24 * 128 * 16;          // one direction's xw of one step: 24 float4 columns x 128 windows (contiguous in HBM)
 constexpr int GR_XST = 2;                          // xw stages PER DIRECTION (a stage never changes its consumer warps)
+constexpr int GR_TW = 120;                         // windows per tile in position-ring mode: 120 rows + 4 look-ahead rows for each of the (at most)
+                                                   // two streams a tile touches fill the 128 rows of a stage buffer
 
 // h (the A operand of the recurrent GEMM) lives in TENSOR MEMORY, fp16 hi (16 columns) + lo (16 columns) per
 // direction; that frees the shared memory for a TMA-filled ring of xw slabs (2 steps x 2 directions x 48 KB).
@@ -661,17 +663,22 @@ __device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
 
 __device__ __forceinline__ void tmem_ldN(uint32_t taddr, float (&v)[8]) { tmem_ld8f(taddr, v); }
 __device__ __forceinline__ void tmem_ldN(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+// per-thread asynchronous 16-byte copy global -> shared (LDGSTS), and an mbarrier arrival that fires when all of the thread's
+// earlier cp.async have landed (it first adds itself to the pending count of the barrier's current phase)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
                "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-// A/B switch (tools/build_variant.sh): the recurrence kernels' issuing warp busy-polls the barriers on the per-step chain
-#ifdef WWB_GR_ISS_SPIN
-#define GR_ISS_WAIT(bar, par) do { while (!mbar_test_wait(bar, par)) { } } while (0)
-#else
+// (A polling wait that keeps calling load_next() so that slab requests go out earlier was measured: 2.53 -> 2.56 ms with the
+// position ring, 2.68 -> 2.74 without - the suspending wait stays.)
 #define GR_ISS_WAIT(bar, par) mbar_wait(bar, par)
-#endif
 
 __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -680,7 +687,20 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role branches are uniform branches
   const int64_t n_win = P.n_win_dev ? (int64_t)*P.n_win_dev : P.n_win;
   const bool shared = P.xws != nullptr;
-  const int64_t n_tiles = (n_win + 127) / 128;
+  // POSITION RING (shared-column mode, streams of >= GR_TW windows).  At step t window j needs column t of its stream = position
+  // m = j + q t of the interior variant: consecutive steps of a tile read position windows that are shifted by q = 8 / hop
+  // (4 at hop 2), so 124 of 128 positions of a step's slab are the previous step's.  Reloading whole slabs was 3.1 GB of
+  // L2 -> SM traffic per launch (probe: the same kernel without the reloads 2.19 instead of 2.68 ms CRNN stage; with the
+  // ring 2.53 - the three whole-slab loads a tile still needs have one step of lead time each).  In ring mode
+  // the interior steps t = 1..17 of a tile and direction share ONE stage buffer as a ring over positions: 128 positions are
+  // loaded once, each later step adds q (row = position modulo the ring size; a tile that touches two streams keeps one
+  // ring per stream: n_A + 4 and n_B + 4 rows of the buffer's 128, hence tiles of 120 windows).  The padded columns
+  // t = 0 / 18 come from their own variants and use the direction's other buffer, loaded while the ring steps run; the two
+  // buffers swap roles from tile to tile so that every large load has a step of lead time.  The barrier protocol is
+  // unchanged: load n may be issued once step n - 2 of the direction has been consumed.
+  const bool ring = shared && P.wps >= GR_TW && P.q == 4;
+  const int TW = ring ? GR_TW : 128;
+  const int64_t n_tiles = (n_win + TW - 1) / TW;
 
   for (int i = tid; i < (int)(2 * GR_U_BYTES / 16); i += GR_THREADS)
     reinterpret_cast<uint4*>(&sm.u[0][0])[i] = reinterpret_cast<const uint4*>(P.u)[i];
@@ -706,10 +726,20 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
     const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + d * 96 + ub;
     const uint32_t th = tmem + ((uint32_t)(q * 32) << 16) + 192 + d * 32 + half * 8;   // this row's h: hi 16 columns, lo 16 columns (2 units per column)
     const float* bh = sm.bh[d] + ub;
-    uint32_t n_acc = 0, n_x = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t b = tile * 128 + r;
-      const bool valid = b < n_win;
+    uint32_t n_acc = 0, n_x = 0, n_tl = 0;   // n_tl: tiles this CTA has started (its parity says which buffer holds the padded-column slabs)
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n_tl) {
+      const int64_t b = tile * TW + r;
+      const bool valid = r < TW && b < n_win;
+      // ring mode: this row's ring (base row, size) and its current row in it
+      int rbase = 0, rsize = 128, ridx = 0;   // (rows past the tile's windows just stay inside the buffer)
+      if (ring) {
+        const int64_t b0 = tile * TW;
+        const int nrows = (int)(n_win - b0 < TW ? n_win - b0 : TW);
+        const int j0 = (int)(b0 % P.wps);
+        const int nA = nrows < P.wps - j0 ? nrows : P.wps - j0;
+        if (r < nA) { rbase = 0; rsize = nA + 4; ridx = r; }
+        else if (r < nrows) { rbase = nA + 4; rsize = nrows - nA + 4; ridx = r - nA; }
+      }
       float h[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) h[i] = 0.f;
@@ -719,7 +749,10 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
         // prefetch only one 400-clock chunk ahead of ~1500 clocks of DRAM latency)
         const int xs = n_x % GR_XST;
         mbar_wait(&sm.x_full[d][xs], (n_x / GR_XST) & 1);
-        const float4* xp = reinterpret_cast<const float4*>(sm.x[d][xs]) + r + (ub / 4) * 128;
+        const bool vstep = s == 0 || s == GR_T - 1;
+        const int xbuf = ring ? (int)((n_tl & 1) ^ (vstep ? 0u : 1u)) : xs;
+        const int xrow = ring && !vstep ? rbase + ridx : r;
+        const float4* xp = reinterpret_cast<const float4*>(sm.x[d][xbuf]) + xrow + (ub / 4) * 128;
         float x_last = 0.f;
         if (s > 0) {
           mbar_wait(&sm.acc_full[d], n_acc & 1);
@@ -761,6 +794,11 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
           tok = __reduce_or_sync(0xffffffffu, tok);
           if (lane == 0) mbar_arrive_after(&sm.x_empty[d][xs], tok);
         }
+        if (ring && !vstep) {   // the next interior step reads q positions further (forward) / back (backward direction)
+          ridx += d ? -4 : 4;
+          if (ridx >= rsize) ridx -= rsize;
+          if (ridx < 0) ridx += rsize;
+        }
         uint32_t hr8[8], lr8[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) split_pair(h[2 * c], h[2 * c + 1], hr8[c], lr8[c]);
@@ -801,6 +839,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
     uint32_t n_ld[2] = {0, 0};          // slabs requested per direction
     int64_t ld_tile[2] = {blockIdx.x, blockIdx.x};
     int ld_s[2] = {0, 0};
+    uint32_t ld_tl[2] = {0, 0};         // tiles whose loads have been started, per direction
     auto load_next = [&](const int dd) {   // requests direction dd's next slab if its stage is free (never blocks)
       if (ld_tile[dd] >= n_tiles) return;
       const int xs = n_ld[dd] % GR_XST;
@@ -810,7 +849,58 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
         if (!__shfl_sync(0xffffffffu, ok, 0)) return;
       }
       const int t = dd ? GR_T - 1 - ld_s[dd] : ld_s[dd];
-      if (shared) {
+      if (ring) {
+        const int s = ld_s[dd];
+        const bool vstep = s == 0 || s == GR_T - 1;
+        unsigned char* const buf = sm.x[dd][(ld_tl[dd] & 1) ^ (vstep ? 0u : 1u)];
+        const int64_t b0 = ld_tile[dd] * TW;
+        const int nrows = (int)(n_win - b0 < TW ? n_win - b0 : TW);
+        const int64_t stream0 = b0 / P.wps;
+        const int j0 = (int)(b0 - stream0 * P.wps);
+        const int nA = nrows < P.wps - j0 ? nrows : P.wps - j0;
+        const int nseg = nrows > nA ? 2 : 1;
+        const unsigned char* base = reinterpret_cast<const unsigned char*>(P.xws) + (t == 0 ? 1 : t == GR_T - 1 ? 2 : 0) * P.xws_variant;
+        const bool full = vstep || s == 1;   // a whole slab: the padded column of the step, or the ring's first 128 positions
+        if (full) {
+          if (lane == 0) mbar_arrive_expect_tx(&sm.x_full[dd][xs], (uint32_t)nrows * 24 * 16);
+          __syncwarp();
+          if (lane < 24) {
+            for (int sg = 0; sg < nseg; ++sg) {
+              const int n = sg ? nrows - nA : nA;                 // windows of this stream in the tile
+              const int j = sg ? 0 : j0;                          // the first one's index in its stream
+              const int rb = vstep ? (sg ? nA : 0) : (sg ? nA + 4 : 0);   // first buffer row of the segment (ring: of its ring)
+              bulk_g2s(buf + ((size_t)lane * 128 + rb) * 16, base + (((size_t)(stream0 + sg) * 48 + dd * 24 + lane) * P.Mp + j + 4 * t) * 16,
+                       (uint32_t)n * 16, &sm.x_full[dd][xs]);
+            }
+          }
+        } else {
+          // Interior step i = s - 1 >= 1: the 4 positions that enter each stream's window, 24 columns each = 96 float4 per
+          // stream, as per-thread 16-byte cp.async (3 per lane and stream) - NOT as bulk copies: the kernel was bound by
+          // the NUMBER of bulk-copy requests (~100 per step at ~90 clk each), not by their bytes.  Virtual index
+          // v = n + 4 (i - 1) + k (forward) or v = -4 i + k (backward), k = 0..3, holds position (first position of the
+          // ring's step 0) + v and lives in row v mod (n + 4).  Each lane's cp.async.mbarrier.arrive adds itself to the
+          // phase's pending count and arrives when the lane's copies have landed; lane 0's plain arrival closes the phase.
+          for (int sg = 0; sg < nseg; ++sg) {
+            const int n = sg ? nrows - nA : nA;
+            const int j = sg ? 0 : j0;
+            const int rb = sg ? nA + 4 : 0;
+            const int i = s - 1, R = n + 4;
+            const int v0 = dd ? -4 * i : n + 4 * (i - 1);
+            const int row0 = ((v0 % R) + R) % R;
+            const int p0 = j + 4 * t + (dd ? 0 : n - 4);          // forward: the last 4 positions of the step's window; backward: its first 4
+#pragma unroll
+            for (int e3 = 0; e3 < 3; ++e3) {
+              const int e = lane + 32 * e3, col = e >> 2, k = e & 3;
+              int row = row0 + k;
+              if (row >= R) row -= R;
+              cp_async16(buf + ((size_t)col * 128 + rb + row) * 16, base + (((size_t)(stream0 + sg) * 48 + dd * 24 + col) * P.Mp + p0 + k) * 16);
+            }
+          }
+          cp_async_mbar_arrive(&sm.x_full[dd][xs]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.x_full[dd][xs]);
+        }
+      } else if (shared) {
         // the tile's windows b0.. are dense over (stream, j): at step t they sit at consecutive positions m = j + q*t of
         // their stream, so a slab is one run of positions per stream the tile touches, times 24 column rows; the padded
         // columns t = 0 / 18 come from their own variants of the strip computation
@@ -834,7 +924,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
                  GR_X_BYTES, &sm.x_full[dd][xs]);
       }
       ++n_ld[dd];
-      if (++ld_s[dd] == GR_T) { ld_s[dd] = 0; ld_tile[dd] += gridDim.x; }
+      if (++ld_s[dd] == GR_T) { ld_s[dd] = 0; ld_tile[dd] += gridDim.x; ++ld_tl[dd]; }
     };
     load_next(0); load_next(1); load_next(0); load_next(1);
     const uint64_t db0 = make_desc(smem_u32(sm.u[0]), 1536, 128), db1 = make_desc(smem_u32(sm.u[1]), 1536, 128);
@@ -896,6 +986,7 @@ int gru_rec_tc(wwb_ctx* ctx, int layer, const float* xw, float* seq_out, float* 
     P.xws = xws;
     P.q = g->q; P.Mp = g->Mp; P.wps = g->wps;
     P.xws_variant = crnn_share_xws_bytes(*g, B / g->wps);
+    if (g->wps >= GR_TW && g->q == 4) n_tiles = (B + GR_TW - 1) / GR_TW;   // position-ring mode (see the kernel)
   }
   P.u = ctx->crnn.tc_u[layer];
   P.bh = ctx->crnn.tc_bh[layer];
