@@ -156,47 +156,68 @@ __global__ void __launch_bounds__(128) crnn_detect_kernel(const float* __restric
                                                           float* __restrict__ out, float* __restrict__ post,
                                                           int64_t B, const int32_t* __restrict__ n_dev) {
   __shared__ float w1s[64][64];
-  __shared__ float es[4][64];
-  __shared__ float hs[4][64];
+  __shared__ float4 es[4][64];      // [warp][k] = input k of the warp's FOUR windows
+  __shared__ float hs[4][4][64];    // [warp][window][unit]
   for (int i = threadIdx.x; i < 64 * 64; i += 128) (&w1s[0][0])[i] = w1t[i];
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const int64_t nB = n_dev ? (int64_t)*n_dev : B;
   __syncthreads();
-  // one window per warp and iteration; the block keeps the 16 KB of W1 in shared memory for all its windows (with one
-  // block per 4 windows, re-staging W1 was 0.9 GB of L2 traffic per bench step and most of the kernel's time)
-  for (int64_t b = (int64_t)blockIdx.x * 4 + wl; b < nB; b += (int64_t)gridDim.x * 4) {
-    es[wl][lane] = enc[b * 64 + lane];
-    es[wl][lane + 32] = enc[b * 64 + 32 + lane];
+  // FOUR windows per warp and iteration: the kernel is bound by shared-memory wavefronts (per input k one broadcast of the
+  // inputs + two rows of W1), and four windows share them (one window per warp: 154 us per 217 088 windows).  The block keeps
+  // the 16 KB of W1 in shared memory for all its windows (with one block per 4 windows, re-staging W1 was 0.9 GB of L2
+  // traffic per bench step and most of the kernel's time).
+  for (int64_t b4 = ((int64_t)blockIdx.x * 4 + wl) * 4; b4 < nB; b4 += (int64_t)gridDim.x * 16) {
+    float e0[4], e1[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const bool live = b4 + w < nB;
+      e0[w] = live ? enc[(b4 + w) * 64 + lane] : 0.f;
+      e1[w] = live ? enc[(b4 + w) * 64 + 32 + lane] : 0.f;
+    }
+    es[wl][lane] = make_float4(e0[0], e0[1], e0[2], e0[3]);
+    es[wl][lane + 32] = make_float4(e1[0], e1[1], e1[2], e1[3]);
     __syncwarp();
-    float a0 = b1[lane], a1 = b1[lane + 32];
+    float a0[4], a1[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { a0[w] = b1[lane]; a1[w] = b1[lane + 32]; }
 #pragma unroll 8
     for (int k = 0; k < 64; ++k) {
-      float e = es[wl][k];
-      a0 = fmaf(w1s[k][lane], e, a0);
-      a1 = fmaf(w1s[k][lane + 32], e, a1);
+      const float4 e = es[wl][k];
+      const float w0 = w1s[k][lane], w1 = w1s[k][lane + 32];
+      a0[0] = fmaf(w0, e.x, a0[0]); a1[0] = fmaf(w1, e.x, a1[0]);
+      a0[1] = fmaf(w0, e.y, a0[1]); a1[1] = fmaf(w1, e.y, a1[1]);
+      a0[2] = fmaf(w0, e.z, a0[2]); a1[2] = fmaf(w1, e.z, a1[2]);
+      a0[3] = fmaf(w0, e.w, a0[3]); a1[3] = fmaf(w1, e.w, a1[3]);
     }
-    hs[wl][lane] = fmaxf(a0, 0.f);
-    hs[wl][lane + 32] = fmaxf(a1, 0.f);
-    __syncwarp();
-    float z[2] = {0.f, 0.f};
-    for (int o = 0; o < n_out; ++o) {
-      float p = w2[o * 64 + lane] * hs[wl][lane];
-      p = fmaf(w2[o * 64 + 32 + lane], hs[wl][lane + 32], p);
 #pragma unroll
-      for (int s = 16; s > 0; s >>= 1) p += __shfl_xor_sync(0xffffffffu, p, s);
-      z[o] = p + b2[o];
+    for (int w = 0; w < 4; ++w) {
+      hs[wl][w][lane] = fmaxf(a0[w], 0.f);
+      hs[wl][w][lane + 32] = fmaxf(a1[w], 0.f);
     }
-    if (lane == 0) {
-      if (n_out == 1) {
-        float p = sigmoid_f(z[0]);
-        if (out) out[b] = p;
-        if (post) post[b] = p;
-      } else {
-        float m = fmaxf(z[0], z[1]);
-        float e0 = expf(z[0] - m), e1 = expf(z[1] - m);
-        float s = e0 + e1;
-        if (out) { out[b * 2] = e0 / s; out[b * 2 + 1] = e1 / s; }
-        if (post) post[b] = e1 / s;
+    __syncwarp();
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int64_t b = b4 + w;
+      float z[2] = {0.f, 0.f};
+      for (int o = 0; o < n_out; ++o) {
+        float p = w2[o * 64 + lane] * hs[wl][w][lane];
+        p = fmaf(w2[o * 64 + 32 + lane], hs[wl][w][lane + 32], p);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) p += __shfl_xor_sync(0xffffffffu, p, s);
+        z[o] = p + b2[o];
+      }
+      if (lane == 0 && b < nB) {
+        if (n_out == 1) {
+          float p = sigmoid_f(z[0]);
+          if (out) out[b] = p;
+          if (post) post[b] = p;
+        } else {
+          float m = fmaxf(z[0], z[1]);
+          float e0_ = expf(z[0] - m), e1_ = expf(z[1] - m);
+          float sden = e0_ + e1_;
+          if (out) { out[b * 2] = e0_ / sden; out[b * 2 + 1] = e1_ / sden; }
+          if (post) post[b] = e1_ / sden;
+        }
       }
     }
     __syncwarp();
@@ -204,7 +225,7 @@ __global__ void __launch_bounds__(128) crnn_detect_kernel(const float* __restric
 }
 
 static unsigned detect_grid(const wwb_ctx* ctx, int64_t B) {
-  return (unsigned)std::min<int64_t>((B + 3) / 4, (int64_t)ctx->sm_count * 16);
+  return (unsigned)std::min<int64_t>((B + 15) / 16, (int64_t)ctx->sm_count * 16);   // 4 warps x 4 windows per block and iteration
 }
 
 int crnn_simt_detect(wwb_ctx* ctx, const float* enc, int64_t B, float* out, cudaStream_t st) {

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
         vn = vn && f < P.wm.ring;
         row = s0 * P.wm.ring + (vn ? f : 0);
         snap_out = vn && (c == 0 || o >= WN_CHUNK_WARM);
-        snap_dst = P.snap + row * WN_SNAP_F;
+        snap_dst = P.snap + row * 4;   // float4 index `row` of plane 0 (planes are n_rows float4 apart)
       } else {
         b = g * WN_G + w;
         vn = vn && (t < L) && (b < n_win);
@@ -228,20 +228,22 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
       }
       valid = vn;
       if (src_slot >= 0) {
-        const float4* p = reinterpret_cast<const float4*>(P.snap + ((int64_t)src_slot * P.n_rows + row) * WN_SNAP_F);
+        // snapshot planes: [slot][12 float4 columns: x 0-3, skip 4-11][n_rows] - the rows of a warp are a handful of consecutive
+        // frames, so each of the 12 loads touches a few sectors (as [row][48 floats] the stream pass's stores were one sector per lane)
+        const float4* p = reinterpret_cast<const float4*>(P.snap) + (int64_t)src_slot * (WN_SNAP_F / 4) * P.n_rows + row;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 v = vn ? __ldg(p + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 v = vn ? __ldg(p + (int64_t)i * P.n_rows) : make_float4(0.f, 0.f, 0.f, 0.f);
           x[2 * i] = pk(v.x, v.y);
           x[2 * i + 1] = pk(v.z, v.w);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sk[i * WN_ROWS] = vn ? __ldg(p + 4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) sk[i * WN_ROWS] = vn ? __ldg(p + (int64_t)(4 + i) * P.n_rows) : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
-        const float4* p = reinterpret_cast<const float4*>(P.x0 + row * 16);
+        const float4* p = reinterpret_cast<const float4*>(P.x0) + row;   // column planes like the snapshots: [4][n_rows] float4
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 v = vn ? __ldg(p + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 v = vn ? __ldg(p + (int64_t)i * P.n_rows) : make_float4(0.f, 0.f, 0.f, 0.f);
           x[2 * i] = pk(v.x, v.y);
           x[2 * i + 1] = pk(v.z, v.w);
         }
@@ -390,16 +392,16 @@ __global__ void __launch_bounds__(WN_THREADS, 1) wavenet_tc_kernel(const WnTcPar
           // stream-level pass: x and the skip prefix sum after this block, for the window tiles that join at block k+1
           const int sl = P.snap_slot[k];
           if (sl >= 0 && snap_g) {
-            float4* dst = reinterpret_cast<float4*>(snap_g_dst + (int64_t)sl * P.n_rows * WN_SNAP_F);
+            float4* dst = reinterpret_cast<float4*>(snap_g_dst) + (int64_t)sl * (WN_SNAP_F / 4) * P.n_rows;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               float a0, a1, a2, a3;
               upk(x[2 * i], a0, a1);
               upk(x[2 * i + 1], a2, a3);
-              dst[i] = make_float4(a0, a1, a2, a3);
+              dst[(int64_t)i * P.n_rows] = make_float4(a0, a1, a2, a3);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[4 + i] = sk[i * WN_ROWS];
+            for (int i = 0; i < 8; ++i) dst[(int64_t)(4 + i) * P.n_rows] = sk[i * WN_ROWS];
           }
         }
         if (last) {
@@ -763,7 +765,8 @@ std::vector<unsigned char> wavenet_pack_head(const float* bn_mul0, const float* 
 }
 
 // Input layer (Wavenet/encode.tflite op 0: 1x1 conv 40 -> 16 + ReLU) once per mel row, fp32:
-// x0[row, c] = ReLU(b[c] + sum_k w[k][c] * mel[row, k]).  4 threads per row, 4 channels each.
+// x0[row, c] = ReLU(b[c] + sum_k w[k][c] * mel[row, k]).  4 threads per row, 4 channels each; stored as 4 column planes
+// of n_rows float4 (the rows a warp of the main kernel reads are a handful of consecutive frames).
 __global__ void __launch_bounds__(256) wn_input_kernel(const float* __restrict__ mel, const float* __restrict__ w_kc,
                                                        const float* __restrict__ b, float* __restrict__ x0, int64_t n_rows) {
   __shared__ float ws[kMel * 16];
@@ -785,7 +788,7 @@ __global__ void __launch_bounds__(256) wn_input_kernel(const float* __restrict__
         a0 = fmaf(wv.x, mv[e], a0); a1 = fmaf(wv.y, mv[e], a1); a2 = fmaf(wv.z, mv[e], a2); a3 = fmaf(wv.w, mv[e], a3);
       }
     }
-    reinterpret_cast<float4*>(x0 + row * 16)[c4] = make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
+    reinterpret_cast<float4*>(x0)[(int64_t)c4 * n_rows + row] = make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));   // plane c4
   }
 }
 

@@ -51,7 +51,7 @@ struct WnTcParams {
   WinMap wm;
   const unsigned char* wblob;   // [24][WN_WBLK]
   const WnHead* head;
-  const float* x0;              // [n_streams * ring][16]: ReLU(in_w * mel + in_b) of every mel row (wn_input_kernel)
+  const float* x0;              // [4 float4 columns][n_streams * ring] float4: ReLU(in_w * mel + in_b) of every mel row (wn_input_kernel)
   int L;
   int nsplit;
   int dil[24];                  // dilation per block (kernel-parameter space keeps it in uniform registers)
@@ -65,7 +65,7 @@ struct WnTcParams {
   // broadcast shared-memory loads they were ~100 wavefronts per warp and group, with all tiles reaching the detect
   // epilogue at about the same time (1900 clk of the ~4900 clk group boundary)
   float det1_b[32], det2_w[64], det2_b[2];
-  float* snap;                  // [n_slots][n_rows][WN_SNAP_F]
+  float* snap;                  // [n_slots][WN_SNAP_F / 4 float4 columns][n_rows] float4 (column planes)
   int64_t n_rows;               // rows behind x0 / snap (n_streams * ring)
   float* enc_out;
   float* det_out;
