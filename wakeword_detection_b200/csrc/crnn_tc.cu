@@ -586,7 +586,7 @@ constexpr int GR_EPI_WARPS = 16;                 // 2 directions x 4 lane quadra
                                                  // recurrences are not bound by per-warp latency but by the operand traffic of a step
                                                  // (layer 1: 96 KB of xw slabs per CTA and step from L2 = 3.2 TB/s over the launch; layer 2: 2 GB of
                                                  // layer-1 output read back from HBM per 512 x 10 s)
-constexpr int GR_THREADS = (GR_EPI_WARPS + 1) * 32;   // + the MMA issuer / loader warp = 544
+constexpr int GR_THREADS = (GR_EPI_WARPS + 2) * 32;   // + the MMA issuer warp + the operand loader warp = 576
 
 constexpr int G2_A_BYTES = 2 * 8 * 128 * 16;       // layer-1 output of 128 windows at one step as a packed fp16 hi/lo operand (K = 64): 32 KB
 constexpr int GR_X_BYTES = 24 * 128 * 16;          // one direction's xw of one step: 24 float4 columns x 128 windows (contiguous in HBM)
@@ -831,11 +831,9 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
         for (int i = 0; i < 4; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
       }
     }
-  } else {
-    // MMA issuer + xw loader
-    const uint32_t idesc = make_idesc_f16(128, 96);
-    const int nsplit = P.nsplit;
-    uint32_t n_h = 0;
+  } else if (warp == GR_EPI_WARPS + 1) {
+    // xw loader: its own warp - as part of the issuing warp the address arithmetic and the copies of a slab request sat
+    // between an h_ready arrival and the step's GEMM issue
     uint32_t n_ld[2] = {0, 0};          // slabs requested per direction
     int64_t ld_tile[2] = {blockIdx.x, blockIdx.x};
     int ld_s[2] = {0, 0};
@@ -926,14 +924,22 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rec_tc_kernel(const GrParam
       ++n_ld[dd];
       if (++ld_s[dd] == GR_T) { ld_s[dd] = 0; ld_tile[dd] += gridDim.x; ++ld_tl[dd]; }
     };
-    load_next(0); load_next(1); load_next(0); load_next(1);
+    while (ld_tile[0] < n_tiles || ld_tile[1] < n_tiles) {
+      const uint32_t before = n_ld[0] + n_ld[1];
+      load_next(0);
+      load_next(1);
+      if (n_ld[0] + n_ld[1] == before) __nanosleep(64);
+    }
+  } else {
+    // MMA issuer
+    const uint32_t idesc = make_idesc_f16(128, 96);
+    const int nsplit = P.nsplit;
+    uint32_t n_h = 0;
     const uint64_t db0 = make_desc(smem_u32(sm.u[0]), 1536, 128), db1 = make_desc(smem_u32(sm.u[1]), 1536, 128);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int s = 1; s < GR_T; ++s, ++n_h) {
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
-          load_next(0);
-          load_next(1);
           GR_ISS_WAIT(&sm.h_ready[d], n_h & 1);
           fence_after_sync();
           if (elect_one()) {
@@ -1145,10 +1151,8 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru2_fused_tc_kernel(const G2Pa
         for (int i = 0; i < 4; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
       }
     }
-  } else {
-    // MMA issuer + slab loader
-    const uint32_t idesc_x = make_idesc_f16(128, 96), idesc_zr = make_idesc_f16(128, 64), idesc_h = make_idesc_f16(128, 32);
-    const int nsplit = P.nsplit;
+  } else if (warp == GR_EPI_WARPS + 1) {
+    // slab loader (its own warp, like in gru_rec_tc_kernel)
     uint32_t n_ld[2] = {0, 0};
     int64_t ld_tile[2] = {blockIdx.x, blockIdx.x};
     int ld_s[2] = {0, 0};
@@ -1168,15 +1172,22 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru2_fused_tc_kernel(const G2Pa
       ++n_ld[dd];
       if (++ld_s[dd] == GR_T) { ld_s[dd] = 0; ld_tile[dd] += gridDim.x; }
     };
-    load_next(0); load_next(1); load_next(0); load_next(1);
+    while (ld_tile[0] < n_tiles || ld_tile[1] < n_tiles) {
+      const uint32_t before = n_ld[0] + n_ld[1];
+      load_next(0);
+      load_next(1);
+      if (n_ld[0] + n_ld[1] == before) __nanosleep(64);
+    }
+  } else {
+    // MMA issuer
+    const uint32_t idesc_x = make_idesc_f16(128, 96), idesc_zr = make_idesc_f16(128, 64), idesc_h = make_idesc_f16(128, 32);
+    const int nsplit = P.nsplit;
     uint32_t n_step = 0, n_h = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int s = 0; s < GR_T; ++s, ++n_step) {
         // input projections of this step (do not depend on h): as soon as the slab is in and the accumulator has been read
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
-          load_next(0);
-          load_next(1);
           const int xs = n_step % G2_AST;
           mbar_wait(&sm.a_full[d][xs], (n_step / G2_AST) & 1);
           if (n_step > 0) GR_ISS_WAIT(&sm.acc_free[d], (n_step - 1) & 1);
@@ -1203,8 +1214,6 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru2_fused_tc_kernel(const G2Pa
         if (s == 0) continue;
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
-          load_next(0);
-          load_next(1);
           GR_ISS_WAIT(&sm.h_ready[d], n_h & 1);
           fence_after_sync();
           if (elect_one()) {
