@@ -122,6 +122,11 @@ __device__ __noinline__ void wn_hang(long long* dbg, int warp, int id, int hk, i
 #define WN_HSET(var, val) do { } while (0)
 #endif
 // busy-poll (no suspension): for the two issuing warps, whose wake-up latency is on every tile's chain
+// Not bounded itself (a poll counter cost 0.7 % of the kernel, 12.96 -> 13.06 ms; checked once per 8 unrolled polls: 13.17):
+// every wait of the two issuing warps is for an arrival that an epilogue warp produces or for a GEMM the other issuing warp
+// issues after such an arrival, and the epilogue warps wait with mbar_wait, which traps after 2^24 retries - a broken
+// protocol still ends as a launch failure, not as a hung GPU (that is how the deadlock of the res/skip-detect variant
+// surfaced, profiles/r2_notes.md).
 __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
   while (!mbar_test_wait(bar, parity)) { }
