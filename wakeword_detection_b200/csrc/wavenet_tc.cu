@@ -4,16 +4,18 @@
 // TIME-MAJOR: (time t, window w) -> o = t*4 + w form the M dimension of every GEMM (6 tiles of 128 rows, 728 of the
 // 768 rows are real; the 64 rows in front of row 0 are the causal zero padding of all four windows).  A dilated tap
 // is still a linear row shift (4*d rows).  Each of the 768 epilogue threads owns ONE row for the whole 24-block
-// stack: its 16-channel residual stream and 32-channel skip sum never leave registers.  (Round 2 ran 3 windows on
-// 5 tiles at 80 registers per thread; 4 on 6 - 832 threads, 72 registers, 80 instead of 96 tensor-memory columns per
-// tile - pays the per-block dependency chain once per 4 windows instead of 3: 15.5 -> 13.9 ms per 512 x 10 s.)
+// stack: its 16-channel residual stream never leaves registers, its 32-channel skip sum lives in the thread's own 128 bytes
+// of shared memory.  (The first half of round 2 ran 3 windows on 5 tiles at 80 registers per thread; 4 on 6 - 832 threads,
+// 72 registers, 80 instead of 96 tensor-memory columns per tile - pays the per-block dependency chain once per 4 windows
+// instead of 3: 15.5 -> 13.5 ms per 512 x 10 s; -> 12.9 with the snapshots stored as column planes.)
 //
 // SHARED ACTIVATIONS (sliding-window batches).  Row t of block b depends on the window's zero padding only while
 // t < D(b) = sum_{m<=b} 2*dilation[m] (2, 6, 14, 30, 32, ... 180): every other activation is a function of the
 // stream's absolute frame and identical in all ~91 windows that cover it.  With time-major rows the window-dependent
 // ("dirty") rows of a block are a PREFIX, so tile i only has to take part from block join[i] = min{b : D(b) > t_min(i)}
 // on (0, 5, 9, 14, 18, 22 for the shipped model: 76 instead of 144 tile-blocks per group).  A tile joins from per-frame
-// SNAPSHOTS (residual stream x and the skip prefix sum after block join[i]-1; 192 B per frame and level) written by a
+// SNAPSHOTS (residual stream x and the skip prefix sum after block join[i]-1; 192 B per frame and level, stored as 12
+// column planes of float4 so that a warp's consecutive frames are consecutive in memory) written by a
 // stream-level pass of this same kernel (stream_mode: a group is a chunk of 768 consecutive frames of one stream,
 // rows o >= 180 of a chunk are past every receptive field; +1.5 % work).  Same MMAs on the same operand values in the
 // same order, so the posteriors are bit-identical to the per-window formulation (WWB_WN_NO_SHARE=1 forces it).

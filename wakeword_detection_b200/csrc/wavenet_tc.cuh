@@ -16,9 +16,9 @@ constexpr int WN_UROWS = WN_ROWS + WN_PAD;
 constexpr int WN_MAXT = 182;                  // WN_G * 182 = 728 rows <= WN_ROWS
 constexpr int WN_CHUNK_WARM = 180;            // stream mode: rows of a chunk inside some receptive field (D(23) = 180)
 constexpr int WN_CHUNK_STEP = WN_ROWS - WN_CHUNK_WARM;
-constexpr int WN_SNAP_F = 48;                 // floats per snapshot row: x[16], skip prefix sum[32]
+constexpr int WN_SNAP_F = 48;                 // floats per snapshot row: x[16], skip prefix sum[32] (stored as 12 float4 column planes)
 constexpr int WN_PU = WN_UROWS * 16;          // bytes per U chunk panel
-constexpr int WN_UBUF = 4 * WN_PU;            // one U buffer: hi and lo planes of two k-chunks
+constexpr int WN_UBUF = 4 * WN_PU;            // the U buffer: hi and lo planes of two k-chunks
 constexpr int WN_EPI_WARPS = WN_NT * 4;       // 24
 constexpr int WN_EPI_THREADS = WN_EPI_WARPS * 32;
 constexpr int WN_THREADS = (WN_EPI_WARPS + 2) * 32;   // + the gate-GEMM / loader warp + the res/skip-GEMM warp = 832
